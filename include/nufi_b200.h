@@ -1,0 +1,166 @@
+/*
+ * nufi_b200.h -- C ABI of libnufi_b200.so, the B200 (sm_100a) implementation of NuFI's hot path:
+ * per time step n, trace every quadrature point (x,v) back through the stored history of potential
+ * spline coefficients (levels n-1..0), evaluate f0 at the foot, reduce into rho; then the field tail
+ * (periodic Poisson solve + spline interpolation) producing level n -- all on the device.
+ *
+ * Boundary being replaced (reference file:line, paulwilhelmvlasov/NumericalFlowIteration):
+ *   nufi::dim{1,2,3}::cuda_scheduler<real,order>   nufi/cuda_scheduler.hpp:33-164, 173-279, 286-392
+ *   nufi::dim{1,2,3}::cuda_kernel<real,order>      nufi/cuda_kernel.hpp:33-56, 77-98, 119-140;
+ *                                                   nufi/cuda_kernel.cu:31-51, 112-189, 210-237, 289-371,
+ *                                                   393-426, 468-573
+ *   and, for the CPU-shaped callers, the loop body of bin/test_nufi_cpu_{1,2,3}d.cpp:
+ *   dimN::eval_rho (nufi/rho.hpp:133-146, 283-310, 428-462), dimN::poisson<double>::solve
+ *   (nufi/poisson.cpp:66-89, 190-219, 328-362), dimN::interpolate (nufi/fields.hpp:63-142, 186-300, 352-490).
+ *
+ * Conventions kept from the reference:
+ *   - nufi_b200_config{1,2,3}d has the memory layout of nufi::dim{1,2,3}::config_t<double>
+ *     (nufi/config.hpp:33-53, 91-114, 167-193); a C++ caller may pass &conf reinterpret_cast.
+ *   - history level m lives at coeffs + m*stride_t, stride_t = prod_d (N_d + order - 1), x fastest
+ *     (nufi/rho.hpp:326-329).  Step n reads levels n-1..1 with full kicks, level 0 with a half kick.
+ *   - flat quadrature index q: 1d q = ix*Nu + iu; 2d q = ((iy*Nx+ix)*Nv+iv)*Nu+iu;
+ *     3d q = ((((iz*Ny+iy)*Nx+ix)*Nw+iw)*Nv+iv)*Nu+iu (nufi/cuda_kernel.cu:40-41, 219-225, 402-412).
+ *   - velocity nodes are midpoints, computed as (u_min + 0.5*du) + i*du with du=(u_max-u_min)/Nu (the CPU
+ *     form, nufi/rho.hpp:137-142) -- the parity target is the reference's CPU eval_rho.
+ *   - compute_rho/download_rho use the reference GPU path's convention: partial rho[l] = -dV * sum f (no
+ *     leading 1), download ACCUMULATES into the caller's array (nufi/cuda_kernel.cu:135-145).
+ *     eval_rho_all / the fused step use the CPU convention rho = 1 - dV * sum f (nufi/rho.hpp:145).
+ *
+ * Every function returns NUFI_B200_OK or an error code; nufi_b200_last_error() gives the message
+ * (the reference throws: cuda::exception -> ERR_CUDA, std::range_error -> ERR_RANGE, std::bad_alloc ->
+ * ERR_ALLOC; nufi/cuda_runtime.hpp:93-98, nufi/cuda_kernel.cu:115-116, 306-307).
+ * Calls on one handle are not re-entrant.  One handle drives one GPU; work is sharded over GPUs by
+ * giving each handle its own [q_begin,q_end) (the reference's partition, nufi/cuda_scheduler.hpp:88-111)
+ * and summing the partial rho vectors (NCCL all-reduce in the host layer).
+ * There is no CPU fallback: without a CUDA device every entry point fails with ERR_CUDA.
+ */
+#ifndef NUFI_B200_H
+#define NUFI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NUFI_B200_OK 0
+#define NUFI_B200_ERR_RANGE 1 /* time step / level / index out of range           (std::range_error) */
+#define NUFI_B200_ERR_CUDA 2  /* CUDA / cuFFT runtime failure, or no device        (cuda::exception)  */
+#define NUFI_B200_ERR_ALLOC 3 /* host or device allocation failed                  (std::bad_alloc)   */
+#define NUFI_B200_ERR_ARG 4   /* invalid or unsupported argument                   (std::invalid_argument) */
+
+typedef struct nufi_b200_handle nufi_b200_handle;
+
+/* nufi::dim1::config_t<double>, nufi/config.hpp:33-53 */
+typedef struct {
+    size_t Nx, Nu, Nt;
+    double dt;
+    double x_min, x_max;
+    double u_min, u_max;
+    double dx, dx_inv, Lx, Lx_inv;
+    double du;
+} nufi_b200_config1d;
+
+/* nufi::dim2::config_t<double>, nufi/config.hpp:91-114 */
+typedef struct {
+    size_t Nx, Ny, Nu, Nv, Nt;
+    double dt;
+    double x_min, x_max, y_min, y_max;
+    double u_min, u_max, v_min, v_max;
+    double dx, dx_inv, Lx, Lx_inv;
+    double dy, dy_inv, Ly, Ly_inv;
+    double du, dv;
+} nufi_b200_config2d;
+
+/* nufi::dim3::config_t<double>, nufi/config.hpp:167-193 */
+typedef struct {
+    size_t Nx, Ny, Nz, Nu, Nv, Nw, Nt;
+    double dt;
+    double x_min, x_max, y_min, y_max, z_min, z_max;
+    double u_min, u_max, v_min, v_max, w_min, w_max;
+    double dx, dx_inv, Lx, Lx_inv;
+    double dy, dy_inv, Ly, Ly_inv;
+    double dz, dz_inv, Lz, Lz_inv;
+    double du, dv, dw;
+} nufi_b200_config3d;
+
+/* Initial condition f0 (static member of config_t in the reference, chosen by editing nufi/config.hpp).
+ *  1d: kind 0 Landau (:83), 1 two-stream (:82);                           p = {alpha, k}
+ *  2d: kind 0 Landau (:148-149), 1 two-stream (:151-158);                 p = {alpha, k, v0}
+ *  3d: kind 0 Landau (:233-234), 1 two-stream (:237-242), 2 bump-on-tail (:244-246); p = {alpha, k, v0}
+ * f0 must be periodic in x with the box (it is for every configuration of the reference). */
+typedef struct {
+    int kind;
+    double p[4];
+} nufi_b200_f0;
+
+/* ---- lifetime (cuda_scheduler ctor, nufi/cuda_scheduler.hpp:43-63; cuda_kernel ctor nufi/cuda_kernel.cu:81-110,
+ *      273-287, 468-483).  Allocates the (Nt+1)-level device history, rho, metrics on `device`
+ *      (-1 = current device).  order must be 4 (cubic; every reference driver instantiates <double,4>). ---- */
+int nufi_b200_create_1d(const nufi_b200_config1d *conf, int order, const nufi_b200_f0 *f0, int device, nufi_b200_handle **out);
+int nufi_b200_create_2d(const nufi_b200_config2d *conf, int order, const nufi_b200_f0 *f0, int device, nufi_b200_handle **out);
+int nufi_b200_create_3d(const nufi_b200_config3d *conf, int order, const nufi_b200_f0 *f0, int device, nufi_b200_handle **out);
+void nufi_b200_destroy(nufi_b200_handle *h);
+/* message of the last failure on h (h == NULL: of the last failed create on this thread) */
+const char *nufi_b200_last_error(const nufi_b200_handle *h);
+
+/* ---- the reference scheduler's five methods ---- */
+/* cuda_kernel::compute_rho (nufi/cuda_kernel.cu:112-132): asynchronous; partial rho over flat q in [q_begin,q_end)
+ * at time step n from device levels 0..n-1.  n > Nt -> ERR_RANGE.  Empty range: rho partial = 0. */
+int nufi_b200_compute_rho(nufi_b200_handle *h, size_t n, size_t q_begin, size_t q_end);
+/* cuda_kernel::download_rho (:135-145): blocking; rho_host[l] += partial[l], l < Nx*Ny*Nz. */
+int nufi_b200_download_rho(nufi_b200_handle *h, double *rho_host);
+/* cuda_kernel::upload_phi (:147-156): blocking; copies level n from the BASE pointer of the host history,
+ * i.e. coeffs_base[n*stride_t .. (n+1)*stride_t). */
+int nufi_b200_upload_phi(nufi_b200_handle *h, size_t n, const double *coeffs_base);
+/* cuda_kernel::compute_metrics / download_metrics (:158-189): eval_f backtrace (needs levels 0..n), then
+ * metrics[0..3] += {int f, int f^2, kinetic energy, entropy}.  Weights as the reference writes them. */
+int nufi_b200_compute_metrics(nufi_b200_handle *h, size_t n, size_t q_begin, size_t q_end);
+int nufi_b200_download_metrics(nufi_b200_handle *h, double *metrics4_host);
+
+/* ---- CPU-driver-shaped entry points (bin/test_nufi_cpu_{1,2,3}d.cpp loop body) ---- */
+/* the whole "#pragma omp parallel for: rho[l] = eval_rho(n,l,coeffs,conf)" sweep in one call; blocking;
+ * CPU convention (leading 1); rho_host may be NULL (result stays on the device for solve_interpolate). */
+int nufi_b200_eval_rho_all(nufi_b200_handle *h, size_t n, double *rho_host);
+/* poisson::solve + interpolate on the device rho left by eval_rho_all / step: writes device level n;
+ * *energy (may be NULL) = return value of solve.  Blocking iff energy != NULL. */
+int nufi_b200_solve_interpolate(nufi_b200_handle *h, size_t n, double *energy);
+/* same, but from a host rho (CPU convention), e.g. after an MPI/host reduction; blocking */
+int nufi_b200_solve_interpolate_host(nufi_b200_handle *h, size_t n, const double *rho_host, double *energy);
+
+/* ---- fused step: backtrace + reduce + Poisson + interpolate + store level n, no host round trip.
+ *      Asynchronous; the electric energy of step n is kept on the device (nufi_b200_download_energy). ---- */
+int nufi_b200_step(nufi_b200_handle *h, size_t n);
+/* blocking; energies[i] = electric energy of step n_begin+i, for steps run by step/solve_interpolate */
+int nufi_b200_download_energy(nufi_b200_handle *h, size_t n_begin, size_t n_end, double *energies);
+/* blocking; level n (stride_t doubles, reference layout with halo) to the host */
+int nufi_b200_download_phi(nufi_b200_handle *h, size_t n, double *coeffs_level);
+int nufi_b200_sync(nufi_b200_handle *h);
+
+/* ---- device-pointer plumbing for one-process-per-GPU callers (torch.distributed / NCCL host layer) ---- */
+/* run all work of h on this cudaStream_t (NULL = the handle's own stream) */
+int nufi_b200_set_stream(nufi_b200_handle *h, void *cuda_stream);
+/* device address of the partial rho (GPU convention, Nx*Ny*Nz doubles) written by compute_rho */
+int nufi_b200_rho_device(nufi_b200_handle *h, double **d_rho);
+/* field tail from a device vector holding the SUM over all shards of the partial rho (GPU convention):
+ * rho = 1 + sum, solve, interpolate, store level n, record energy[n].  Asynchronous. */
+int nufi_b200_field_tail_device(nufi_b200_handle *h, size_t n, const double *d_rho_partial_sum);
+
+/* ---- introspection used by bench.py / tests ---- */
+/* number of kernels this library launched on h since creation */
+uint64_t nufi_b200_launch_count(const nufi_b200_handle *h);
+/* GPU time in ms of the most recent backtrace kernel (CUDA events on the launching stream); blocking */
+int nufi_b200_last_backtrace_ms(nufi_b200_handle *h, float *ms);
+/* which kernel variant the last compute_rho used: writes a short static string ("smem-tma", "global") */
+const char *nufi_b200_last_variant(const nufi_b200_handle *h);
+/* force a variant for A/B tests: 0 auto, 1 global-memory path, 2 shared-memory staged path */
+int nufi_b200_set_variant(nufi_b200_handle *h, int variant);
+/* register-only DFMA loop on `device`: measured FP64 peak in TFLOP/s (FMA = 2 flop) */
+int nufi_b200_measure_fp64_peak(int device, double *tflops);
+const char *nufi_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NUFI_B200_H */

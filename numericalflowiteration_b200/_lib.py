@@ -1,0 +1,70 @@
+"""ctypes binding of libnufi_b200.so (include/nufi_b200.h).  Fails loudly when the CUDA library is missing:
+there is no CPU or PyTorch fallback for the hot path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libnufi_b200.so")
+
+OK, ERR_RANGE, ERR_CUDA, ERR_ALLOC, ERR_ARG = 0, 1, 2, 3, 4
+
+# every symbol include/nufi_b200.h declares (tests check the library exports exactly these)
+SYMBOLS = [
+    "nufi_b200_create_1d", "nufi_b200_create_2d", "nufi_b200_create_3d", "nufi_b200_destroy", "nufi_b200_last_error",
+    "nufi_b200_compute_rho", "nufi_b200_download_rho", "nufi_b200_upload_phi", "nufi_b200_compute_metrics",
+    "nufi_b200_download_metrics", "nufi_b200_eval_rho_all", "nufi_b200_solve_interpolate",
+    "nufi_b200_solve_interpolate_host", "nufi_b200_step", "nufi_b200_download_energy", "nufi_b200_download_phi",
+    "nufi_b200_sync", "nufi_b200_set_stream", "nufi_b200_rho_device", "nufi_b200_field_tail_device",
+    "nufi_b200_launch_count", "nufi_b200_last_backtrace_ms", "nufi_b200_last_variant", "nufi_b200_set_variant",
+    "nufi_b200_measure_fp64_peak", "nufi_b200_version",
+]
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(HERE, "csrc"), "-j4"] + ([] if verbose else ["-s"])
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(numericalflowiteration_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, dp, i = C.c_void_p, C.c_size_t, C.POINTER(C.c_double), C.c_int
+    for d in (1, 2, 3):
+        f = getattr(L, f"nufi_b200_create_{d}d")
+        f.argtypes = [vp, i, vp, i, C.POINTER(vp)]
+        f.restype = i
+    L.nufi_b200_destroy.argtypes = [vp]
+    L.nufi_b200_destroy.restype = None
+    L.nufi_b200_last_error.argtypes = [vp]
+    L.nufi_b200_last_error.restype = C.c_char_p
+    for name, args in {
+        "compute_rho": [vp, sz, sz, sz], "download_rho": [vp, vp], "upload_phi": [vp, sz, vp],
+        "compute_metrics": [vp, sz, sz, sz], "download_metrics": [vp, vp], "eval_rho_all": [vp, sz, vp],
+        "solve_interpolate": [vp, sz, vp], "solve_interpolate_host": [vp, sz, vp, vp], "step": [vp, sz],
+        "download_energy": [vp, sz, sz, vp], "download_phi": [vp, sz, vp], "sync": [vp], "set_stream": [vp, vp],
+        "rho_device": [vp, C.POINTER(vp)], "field_tail_device": [vp, sz, vp], "last_backtrace_ms": [vp, C.POINTER(C.c_float)],
+        "set_variant": [vp, i], "measure_fp64_peak": [i, dp],
+    }.items():
+        f = getattr(L, "nufi_b200_" + name)
+        f.argtypes = args
+        f.restype = i
+    L.nufi_b200_launch_count.argtypes = [vp]
+    L.nufi_b200_launch_count.restype = C.c_uint64
+    L.nufi_b200_last_variant.argtypes = [vp]
+    L.nufi_b200_last_variant.restype = C.c_char_p
+    L.nufi_b200_version.restype = C.c_char_p
+    _lib = L
+    return L

@@ -1,0 +1,399 @@
+// api.cu -- the C ABI of libnufi_b200.so (include/nufi_b200.h).  Owns all device state of one GPU:
+// the (Nt+1)-level coefficient history in the device level format, rho, metrics, energies, FFT plans.
+// Mirrors the surface of nufi::dim{1,2,3}::cuda_kernel (nufi/cuda_kernel.cu:81-189, 273-371, 468-573).
+#include "internal.cuh"
+
+#include <cstring>
+#include <new>
+
+namespace nufi_b200
+{
+
+static thread_local std::string g_create_error;
+
+int fail(Handle *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+namespace
+{
+
+void free_all(Handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    tail_destroy(h);
+    cudaFree(h->d_hist); cudaFree(h->d_raw);
+    cudaFree(h->d_rho_partial); cudaFree(h->d_rho_full); cudaFree(h->d_partials);
+    cudaFree(h->d_metrics); cudaFree(h->d_mpartials); cudaFree(h->d_energy); cudaFree(h->d_stage);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int create_common(const nufi_b200_config3d &c, int dim, int order, const nufi_b200_f0 *f0, int device, nufi_b200_handle **out)
+{
+    if (!out) return fail(nullptr, NUFI_B200_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (order != 4)
+        return fail(nullptr, NUFI_B200_ERR_ARG, "only order 4 (cubic B-splines) is implemented; every reference driver uses <double,4>");
+    if (c.Nx < 4 || (dim >= 2 && c.Ny < 4) || (dim >= 3 && c.Nz < 4) || c.Nu == 0 || (dim >= 2 && c.Nv == 0) || (dim >= 3 && c.Nw == 0))
+        return fail(nullptr, NUFI_B200_ERR_ARG, "grid too small: need N >= 4 nodes per spatial dimension and >= 1 velocity node");
+    if (c.Nx > (1u << 20) || c.Ny > (1u << 20) || c.Nz > (1u << 20))
+        return fail(nullptr, NUFI_B200_ERR_ARG, "grid too large");
+    if (!f0 || f0->kind < 0 || f0->kind > (dim == 3 ? 2 : 1)) return fail(nullptr, NUFI_B200_ERR_ARG, "unknown f0 kind");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, NUFI_B200_ERR_CUDA,
+                    std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                        " (libnufi_b200 has no CPU fallback)");
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= ndev) return fail(nullptr, NUFI_B200_ERR_ARG, "device index out of range");
+
+    Handle *h = new (std::nothrow) Handle;
+    if (!h) return fail(nullptr, NUFI_B200_ERR_ALLOC, "out of host memory");
+    h->dim = dim; h->order = order; h->device = device; h->c = c; h->f0 = *f0; h->Nt = c.Nt;
+    h->n_nodes = c.Nx * c.Ny * c.Nz;
+    h->n_vel = c.Nu * c.Nv * c.Nw;
+    h->stride_t = (c.Nx + 3) * (dim >= 2 ? c.Ny + 3 : 1) * (dim >= 3 ? c.Nz + 3 : 1);
+    // device level format
+    if (dim == 1) {
+        h->Nxp = static_cast<int>((c.Nx + 1) & ~size_t(1));
+        h->level_stride = 3 * static_cast<size_t>(h->Nxp);
+        h->raw_stride = (c.Nx + 3 + 1) & ~size_t(1);
+        h->sx = h->Nxp; h->sxy = 0;
+    } else {
+        h->sx = static_cast<int>(c.Nx + 3);
+        h->sxy = h->sx * static_cast<int>(c.Ny + 3);
+        size_t ls = static_cast<size_t>(h->sxy) * (dim == 3 ? c.Nz + 3 : 1);
+        h->level_stride = (ls + 1) & ~size_t(1); // multiple of 16 bytes for the bulk copies
+    }
+    h->level_valid.assign(c.Nt + 1, 0);
+
+#define CREATE_CHECK(expr)                                                                                      \
+    do {                                                                                                        \
+        cudaError_t e__ = (expr);                                                                               \
+        if (e__ != cudaSuccess) {                                                                               \
+            std::string m = std::string(cudaGetErrorName(e__)) + ": " + cudaGetErrorString(e__) + " [" #expr "]"; \
+            int code = (e__ == cudaErrorMemoryAllocation) ? NUFI_B200_ERR_ALLOC : NUFI_B200_ERR_CUDA;           \
+            free_all(h);                                                                                        \
+            cudaGetLastError();                                                                                 \
+            return fail(nullptr, code, m);                                                                      \
+        }                                                                                                       \
+    } while (0)
+
+    CREATE_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CREATE_CHECK(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    CREATE_CHECK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    CREATE_CHECK(cudaEventCreate(&h->ev0));
+    CREATE_CHECK(cudaEventCreate(&h->ev1));
+    const size_t hist_bytes = (c.Nt + 1) * h->level_stride * sizeof(double);
+    CREATE_CHECK(cudaMalloc(&h->d_hist, hist_bytes));
+    CREATE_CHECK(cudaMemsetAsync(h->d_hist, 0, hist_bytes, h->stream));
+    if (dim == 1) {
+        CREATE_CHECK(cudaMalloc(&h->d_raw, (c.Nt + 1) * h->raw_stride * sizeof(double)));
+        CREATE_CHECK(cudaMemsetAsync(h->d_raw, 0, (c.Nt + 1) * h->raw_stride * sizeof(double), h->stream));
+    }
+    CREATE_CHECK(cudaMalloc(&h->d_rho_partial, h->n_nodes * sizeof(double)));
+    CREATE_CHECK(cudaMalloc(&h->d_rho_full, h->n_nodes * sizeof(double)));
+    CREATE_CHECK(cudaMemsetAsync(h->d_rho_partial, 0, h->n_nodes * sizeof(double), h->stream));
+    CREATE_CHECK(cudaMemsetAsync(h->d_rho_full, 0, h->n_nodes * sizeof(double), h->stream));
+    CREATE_CHECK(cudaMalloc(&h->d_metrics, 4 * sizeof(double)));
+    CREATE_CHECK(cudaMemsetAsync(h->d_metrics, 0, 4 * sizeof(double), h->stream));
+    CREATE_CHECK(cudaMalloc(&h->d_mpartials, 4 * sizeof(double) * h->sm_count));
+    CREATE_CHECK(cudaMalloc(&h->d_energy, (c.Nt + 1) * sizeof(double)));
+    CREATE_CHECK(cudaMemsetAsync(h->d_energy, 0, (c.Nt + 1) * sizeof(double), h->stream));
+    CREATE_CHECK(cudaMalloc(&h->d_stage, h->stride_t * sizeof(double)));
+    h->h_pinned_cap = h->stride_t > h->n_nodes ? h->stride_t : h->n_nodes;
+    if (h->h_pinned_cap < c.Nt + 1) h->h_pinned_cap = c.Nt + 1;
+    CREATE_CHECK(cudaMallocHost(&h->h_pinned, h->h_pinned_cap * sizeof(double)));
+#undef CREATE_CHECK
+    int rc = tail_init(h);
+    if (rc != NUFI_B200_OK) {
+        std::string m = h->err;
+        free_all(h);
+        return fail(nullptr, rc, m);
+    }
+    cudaStreamSynchronize(h->stream);
+    *out = reinterpret_cast<nufi_b200_handle *>(h);
+    return NUFI_B200_OK;
+}
+
+inline Handle *H(nufi_b200_handle *h) { return reinterpret_cast<Handle *>(h); }
+inline const Handle *H(const nufi_b200_handle *h) { return reinterpret_cast<const Handle *>(h); }
+
+int check_levels(Handle *h, size_t first_needed_exclusive_end, const char *what)
+{
+    for (size_t m = 0; m < first_needed_exclusive_end; ++m)
+        if (!h->level_valid[m])
+            return fail(h, NUFI_B200_ERR_RANGE, std::string(what) + ": history level " + std::to_string(m) +
+                                                    " was never uploaded or computed");
+    return NUFI_B200_OK;
+}
+
+} // namespace
+} // namespace nufi_b200
+
+using namespace nufi_b200;
+
+#define ENTER(h)                                                         \
+    Handle *hh = H(h);                                                   \
+    if (!hh) return fail(nullptr, NUFI_B200_ERR_ARG, "handle is NULL");  \
+    NUFI_CUDA_CHECK(hh, cudaSetDevice(hh->device))
+
+extern "C" {
+
+int nufi_b200_create_1d(const nufi_b200_config1d *conf, int order, const nufi_b200_f0 *f0, int device, nufi_b200_handle **out)
+{
+    if (!conf) return fail(nullptr, NUFI_B200_ERR_ARG, "conf is NULL");
+    nufi_b200_config3d c{};
+    c.Nx = conf->Nx; c.Ny = 1; c.Nz = 1; c.Nu = conf->Nu; c.Nv = 1; c.Nw = 1; c.Nt = conf->Nt; c.dt = conf->dt;
+    c.x_min = conf->x_min; c.x_max = conf->x_max; c.u_min = conf->u_min; c.u_max = conf->u_max;
+    c.dx = conf->dx; c.dx_inv = conf->dx_inv; c.Lx = conf->Lx; c.Lx_inv = conf->Lx_inv; c.du = conf->du;
+    c.dy = c.dz = c.dy_inv = c.dz_inv = c.Ly = c.Lz = c.Ly_inv = c.Lz_inv = 1; c.dv = c.dw = 1;
+    c.v_max = c.w_max = 1;
+    return create_common(c, 1, order, f0, device, out);
+}
+
+int nufi_b200_create_2d(const nufi_b200_config2d *conf, int order, const nufi_b200_f0 *f0, int device, nufi_b200_handle **out)
+{
+    if (!conf) return fail(nullptr, NUFI_B200_ERR_ARG, "conf is NULL");
+    nufi_b200_config3d c{};
+    c.Nx = conf->Nx; c.Ny = conf->Ny; c.Nz = 1; c.Nu = conf->Nu; c.Nv = conf->Nv; c.Nw = 1; c.Nt = conf->Nt; c.dt = conf->dt;
+    c.x_min = conf->x_min; c.x_max = conf->x_max; c.y_min = conf->y_min; c.y_max = conf->y_max;
+    c.u_min = conf->u_min; c.u_max = conf->u_max; c.v_min = conf->v_min; c.v_max = conf->v_max;
+    c.dx = conf->dx; c.dx_inv = conf->dx_inv; c.Lx = conf->Lx; c.Lx_inv = conf->Lx_inv;
+    c.dy = conf->dy; c.dy_inv = conf->dy_inv; c.Ly = conf->Ly; c.Ly_inv = conf->Ly_inv;
+    c.du = conf->du; c.dv = conf->dv;
+    c.dz = c.dz_inv = c.Lz = c.Lz_inv = 1; c.dw = 1; c.w_max = 1;
+    return create_common(c, 2, order, f0, device, out);
+}
+
+int nufi_b200_create_3d(const nufi_b200_config3d *conf, int order, const nufi_b200_f0 *f0, int device, nufi_b200_handle **out)
+{
+    if (!conf) return fail(nullptr, NUFI_B200_ERR_ARG, "conf is NULL");
+    return create_common(*conf, 3, order, f0, device, out);
+}
+
+void nufi_b200_destroy(nufi_b200_handle *h) { free_all(H(h)); }
+
+const char *nufi_b200_last_error(const nufi_b200_handle *h) { return h ? H(h)->err.c_str() : g_create_error.c_str(); }
+
+int nufi_b200_compute_rho(nufi_b200_handle *h, size_t n, size_t q_begin, size_t q_end)
+{
+    ENTER(h);
+    if (n > hh->Nt) return fail(hh, NUFI_B200_ERR_RANGE, "Time-step out of range."); // cuda_kernel.cu:115-116
+    const size_t nq = hh->n_nodes * hh->n_vel;
+    if (q_begin > q_end || q_end > nq) return fail(hh, NUFI_B200_ERR_RANGE, "quadrature range out of bounds");
+    if (q_begin == q_end) { // reference: no-op after the scheduler's early return; the partial is defined as zero
+        NUFI_CUDA_CHECK(hh, cudaMemsetAsync(hh->d_rho_partial, 0, sizeof(double) * hh->n_nodes, hh->stream));
+        return NUFI_B200_OK;
+    }
+    int rc = check_levels(hh, n, "compute_rho");
+    if (rc) return rc;
+    return launch_backtrace(hh, n, q_begin, q_end, false);
+}
+
+int nufi_b200_download_rho(nufi_b200_handle *h, double *rho_host)
+{
+    ENTER(h);
+    if (!rho_host) return fail(hh, NUFI_B200_ERR_ARG, "rho_host is NULL");
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(hh->h_pinned, hh->d_rho_partial, sizeof(double) * hh->n_nodes, cudaMemcpyDeviceToHost, hh->stream));
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    for (size_t i = 0; i < hh->n_nodes; ++i) rho_host[i] += hh->h_pinned[i]; // cuda_kernel.cu:143-144
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_upload_phi(nufi_b200_handle *h, size_t n, const double *coeffs_base)
+{
+    ENTER(h);
+    if (n > hh->Nt) return fail(hh, NUFI_B200_ERR_RANGE, "Time-step out of range.");
+    if (!coeffs_base) return fail(hh, NUFI_B200_ERR_ARG, "coeffs is NULL");
+    std::memcpy(hh->h_pinned, coeffs_base + n * hh->stride_t, sizeof(double) * hh->stride_t); // slice n (cuda_kernel.cu:154-155)
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(hh->d_stage, hh->h_pinned, sizeof(double) * hh->stride_t, cudaMemcpyHostToDevice, hh->stream));
+    int rc = convert_level_to_device(hh, n, hh->d_stage);
+    if (rc) return rc;
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream)); // blocking, like cudaMemcpy in the reference
+    hh->level_valid[n] = 1;
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_compute_metrics(nufi_b200_handle *h, size_t n, size_t q_begin, size_t q_end)
+{
+    ENTER(h);
+    if (n > hh->Nt) return fail(hh, NUFI_B200_ERR_RANGE, "Time-step out of range.");
+    const size_t nq = hh->n_nodes * hh->n_vel;
+    if (q_begin > q_end || q_end > nq) return fail(hh, NUFI_B200_ERR_RANGE, "quadrature range out of bounds");
+    if (q_begin == q_end) {
+        NUFI_CUDA_CHECK(hh, cudaMemsetAsync(hh->d_metrics, 0, sizeof(double) * 4, hh->stream));
+        return NUFI_B200_OK;
+    }
+    int rc = check_levels(hh, n == 0 ? 0 : n + 1, "compute_metrics");
+    if (rc) return rc;
+    return launch_backtrace(hh, n, q_begin, q_end, true);
+}
+
+int nufi_b200_download_metrics(nufi_b200_handle *h, double *m)
+{
+    ENTER(h);
+    if (!m) return fail(hh, NUFI_B200_ERR_ARG, "metrics is NULL");
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(hh->h_pinned, hh->d_metrics, sizeof(double) * 4, cudaMemcpyDeviceToHost, hh->stream));
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    for (int i = 0; i < 4; ++i) m[i] += hh->h_pinned[i]; // accumulate (cuda_kernel.cu:186-188)
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_eval_rho_all(nufi_b200_handle *h, size_t n, double *rho_host)
+{
+    ENTER(h);
+    if (n > hh->Nt) return fail(hh, NUFI_B200_ERR_RANGE, "Time-step out of range.");
+    int rc = check_levels(hh, n, "eval_rho_all");
+    if (rc) return rc;
+    rc = launch_backtrace(hh, n, 0, hh->n_nodes * hh->n_vel, false);
+    if (rc) return rc;
+    if (rho_host) {
+        NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(hh->h_pinned, hh->d_rho_full, sizeof(double) * hh->n_nodes, cudaMemcpyDeviceToHost, hh->stream));
+        NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+        std::memcpy(rho_host, hh->h_pinned, sizeof(double) * hh->n_nodes);
+    }
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_solve_interpolate(nufi_b200_handle *h, size_t n, double *energy)
+{
+    ENTER(h);
+    if (n > hh->Nt) return fail(hh, NUFI_B200_ERR_RANGE, "Time-step out of range.");
+    int rc = tail_run(hh, n, hh->d_rho_full);
+    if (rc) return rc;
+    if (energy) {
+        NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(hh->h_pinned, hh->d_energy + n, sizeof(double), cudaMemcpyDeviceToHost, hh->stream));
+        NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+        *energy = hh->h_pinned[0];
+    }
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_solve_interpolate_host(nufi_b200_handle *h, size_t n, const double *rho_host, double *energy)
+{
+    ENTER(h);
+    if (!rho_host) return fail(hh, NUFI_B200_ERR_ARG, "rho_host is NULL");
+    std::memcpy(hh->h_pinned, rho_host, sizeof(double) * hh->n_nodes);
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(hh->d_rho_full, hh->h_pinned, sizeof(double) * hh->n_nodes, cudaMemcpyHostToDevice, hh->stream));
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream)); // h_pinned is reused below
+    double e = 0;
+    int rc = nufi_b200_solve_interpolate(h, n, &e);
+    if (rc) return rc;
+    if (energy) *energy = e;
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_step(nufi_b200_handle *h, size_t n)
+{
+    ENTER(h);
+    if (n > hh->Nt) return fail(hh, NUFI_B200_ERR_RANGE, "Time-step out of range.");
+    int rc = check_levels(hh, n, "step");
+    if (rc) return rc;
+    rc = launch_backtrace(hh, n, 0, hh->n_nodes * hh->n_vel, false);
+    if (rc) return rc;
+    return tail_run(hh, n, hh->d_rho_full);
+}
+
+int nufi_b200_download_energy(nufi_b200_handle *h, size_t n_begin, size_t n_end, double *energies)
+{
+    ENTER(h);
+    if (n_begin > n_end || n_end > hh->Nt + 1) return fail(hh, NUFI_B200_ERR_RANGE, "energy range out of bounds");
+    if (n_begin == n_end) return NUFI_B200_OK;
+    if (!energies) return fail(hh, NUFI_B200_ERR_ARG, "energies is NULL");
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(hh->h_pinned, hh->d_energy + n_begin, sizeof(double) * (n_end - n_begin), cudaMemcpyDeviceToHost, hh->stream));
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    std::memcpy(energies, hh->h_pinned, sizeof(double) * (n_end - n_begin));
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_download_phi(nufi_b200_handle *h, size_t n, double *coeffs_level)
+{
+    ENTER(h);
+    if (n > hh->Nt) return fail(hh, NUFI_B200_ERR_RANGE, "Time-step out of range.");
+    if (!coeffs_level) return fail(hh, NUFI_B200_ERR_ARG, "coeffs_level is NULL");
+    int rc = convert_level_from_device(hh, n, hh->d_stage);
+    if (rc) return rc;
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(hh->h_pinned, hh->d_stage, sizeof(double) * hh->stride_t, cudaMemcpyDeviceToHost, hh->stream));
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    std::memcpy(coeffs_level, hh->h_pinned, sizeof(double) * hh->stride_t);
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_sync(nufi_b200_handle *h)
+{
+    ENTER(h);
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_set_stream(nufi_b200_handle *h, void *cuda_stream)
+{
+    ENTER(h);
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    hh->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : hh->own_stream;
+    hh->ev_valid = false;
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_rho_device(nufi_b200_handle *h, double **d_rho)
+{
+    ENTER(h);
+    if (!d_rho) return fail(hh, NUFI_B200_ERR_ARG, "d_rho is NULL");
+    *d_rho = hh->d_rho_partial;
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_field_tail_device(nufi_b200_handle *h, size_t n, const double *d_rho_partial_sum)
+{
+    ENTER(h);
+    if (n > hh->Nt) return fail(hh, NUFI_B200_ERR_RANGE, "Time-step out of range.");
+    if (!d_rho_partial_sum) return fail(hh, NUFI_B200_ERR_ARG, "d_rho_partial_sum is NULL");
+    int rc = make_full_rho(hh, d_rho_partial_sum, hh->d_rho_full);
+    if (rc) return rc;
+    return tail_run(hh, n, hh->d_rho_full);
+}
+
+uint64_t nufi_b200_launch_count(const nufi_b200_handle *h) { return h ? H(h)->launches : 0; }
+
+int nufi_b200_last_backtrace_ms(nufi_b200_handle *h, float *ms)
+{
+    ENTER(h);
+    if (!ms) return fail(hh, NUFI_B200_ERR_ARG, "ms is NULL");
+    if (!hh->ev_valid) return fail(hh, NUFI_B200_ERR_RANGE, "no backtrace kernel has been launched on this stream yet");
+    NUFI_CUDA_CHECK(hh, cudaEventSynchronize(hh->ev1));
+    NUFI_CUDA_CHECK(hh, cudaEventElapsedTime(ms, hh->ev0, hh->ev1));
+    return NUFI_B200_OK;
+}
+
+const char *nufi_b200_last_variant(const nufi_b200_handle *h) { return h ? H(h)->last_variant : "none"; }
+
+int nufi_b200_set_variant(nufi_b200_handle *h, int variant)
+{
+    Handle *hh = H(h);
+    if (!hh) return fail(nullptr, NUFI_B200_ERR_ARG, "handle is NULL");
+    if (variant < 0 || variant > 2) return fail(hh, NUFI_B200_ERR_ARG, "variant must be 0 (auto), 1 (global) or 2 (staged)");
+    hh->variant_force = variant;
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_measure_fp64_peak(int device, double *tflops) { return measure_fp64_peak(device, tflops); }
+
+const char *nufi_b200_version(void) { return "nufi_b200 0.1 (sm_100a)"; }
+
+} // extern "C"

@@ -1,0 +1,124 @@
+// internal.cuh -- shared declarations of libnufi_b200 (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cufft.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/nufi_b200.h"
+
+namespace nufi_b200
+{
+
+// ----------------------------------------------------------------------------------------------
+// Backtrace kernel parameters.  Positions are carried per dimension as (cell k, centred offset
+// tau in [-1/2,1/2]) with xi = (x - x_min)/dx = k + 1/2 + tau; velocities stay physical.
+// ----------------------------------------------------------------------------------------------
+struct BtParams
+{
+    int dim;
+    int Nx, Ny, Nz, Nu, Nv, Nw;
+    int sx, sxy;                     // row / plane stride of a device level (doubles)
+    unsigned long long level_stride; // doubles between consecutive device levels
+    const double *hist;              // device history, device level format
+    int first_level;                 // newest level read: n-1 (rho) or n (metrics); -1: none
+    int metrics;                     // 0: eval_ftilda -> rho partials; 1: eval_f -> metric partials
+    double cx, cy, cz;               // dt*dx_inv: cells per step per unit velocity
+    double gx, gy, gz;               // kick factor -dt*dx_inv / (12 | 72) (2d | 3d basis scaling folded in)
+    double x_min, y_min, z_min, dx, dy, dz;
+    double u0, v0, w0, du, dv, dw;   // first midpoint velocity node and spacing, computed as rho.hpp does
+    double ug0, vg0, wg0, dug, dvg, dwg; // metrics: GPU-form nodes u_min + i*du + du/2 (conf.du)
+    int f0_kind;
+    double f0p[4];
+    // work decomposition (see backtrace.cu)
+    unsigned long long q_begin, q_end, Nvel;
+    unsigned long long l_first;      // first spatial node touched by [q_begin,q_end)
+    unsigned long long l_last;       // last spatial node touched
+    unsigned long long units_per_tile, n_units;
+    unsigned int n_tiles, rounds, W;
+    double *partials;                // [(grid + n_tiles) * W][32]      (rho)
+    double *mpartials;               // [grid][4]                       (metrics)
+    double mweight;
+    int stages;                      // shared-memory ring depth (staged variant)
+    unsigned int level_bytes;        // bytes of one device level (multiple of 16)
+};
+
+struct FinishParams
+{
+    const double *partials;
+    double *rho_partial; // GPU convention: -dV * sum
+    double *rho_full;    // CPU convention: 1 - dV * sum  (may be nullptr)
+    double dV;
+    unsigned long long l_first, l_last, n_nodes_total;
+    unsigned long long units_per_tile;
+    unsigned int n_tiles, rounds, W, grid;
+};
+
+struct Handle
+{
+    int dim = 0, order = 4, device = 0;
+    nufi_b200_config3d c{}; // superset; unused dimensions have N = 1
+    nufi_b200_f0 f0{};
+    size_t Nt = 0;
+    size_t n_nodes = 0, n_vel = 0, stride_t = 0; // reference-format level size
+    // device level format
+    int sx = 0, sxy = 0, Nxp = 0;
+    size_t level_stride = 0; // doubles
+    size_t raw_stride = 0;   // 1d only: raw spline level kept beside the pp-form (doubles)
+    double *d_hist = nullptr, *d_raw = nullptr;
+    std::vector<unsigned char> level_valid;
+    // rho / reduction
+    double *d_rho_partial = nullptr, *d_rho_full = nullptr, *d_partials = nullptr;
+    size_t partials_cap = 0; // doubles
+    double *d_metrics = nullptr, *d_mpartials = nullptr;
+    double *d_energy = nullptr; // [Nt+1]
+    double *d_stage = nullptr;  // device staging for one reference-format level
+    double *h_pinned = nullptr; // pinned host staging (max(stride_t, n_nodes) doubles)
+    size_t h_pinned_cap = 0;
+    // tail
+    cufftHandle plan_fwd = 0, plan_inv = 0;
+    bool plans = false;
+    cufftDoubleComplex *d_spec = nullptr;
+    double *d_symbol = nullptr; // real part tables, see tail.cu
+    double *d_field = nullptr;
+    double *d_epart = nullptr;
+    size_t n_spec = 0;
+    // streams / events
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    int variant_force = 0;
+    const char *last_variant = "none";
+    uint64_t launches = 0;
+    std::string err;
+};
+
+// error helpers (api.cu)
+int fail(Handle *h, int code, const std::string &msg);
+#define NUFI_CUDA_CHECK(h, expr)                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return ::nufi_b200::fail((h), NUFI_B200_ERR_CUDA,                                         \
+                                     std::string(cudaGetErrorName(e__)) + ": " + cudaGetErrorString(e__) + \
+                                         " [" #expr "]");                                             \
+    } while (0)
+
+// backtrace.cu
+int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool metrics);
+// tail.cu
+int tail_init(Handle *h);
+void tail_destroy(Handle *h);
+int tail_run(Handle *h, size_t n, const double *d_rho_full);
+int convert_level_to_device(Handle *h, size_t n, const double *d_ref_level);  // reference format -> device format
+int convert_level_from_device(Handle *h, size_t n, double *d_ref_level);      // device format -> reference format
+int make_full_rho(Handle *h, const double *d_partial_sum, double *d_full);    // full = 1 + partial
+// peak.cu
+int measure_fp64_peak(int device, double *tflops);
+
+} // namespace nufi_b200

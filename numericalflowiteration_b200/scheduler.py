@@ -1,0 +1,193 @@
+"""Host-side mirror of ``nufi::dim{1,2,3}::cuda_scheduler<double,4>`` (reference nufi/cuda_scheduler.hpp:33-164,
+173-279, 286-392) over the C ABI of libnufi_b200.so.
+
+Same five methods with the same argument meaning and error behaviour (``compute_rho``, ``download_rho``,
+``upload_phi``, ``compute_metrics``, ``download_metrics``), plus the CPU-driver-shaped calls
+(``eval_rho`` sweep, ``solve``, ``interpolate``) and the fused ``step`` that removes the host round trip of
+bin/test_nufi_gpu_3d.cpp:154-162.  One scheduler drives one GPU; several GPUs = several processes, each with
+its own q-range (see :mod:`numericalflowiteration_b200.distributed`).
+
+Exceptions: :class:`CudaError` ~ ``nufi::cuda::exception`` (nufi/cuda_runtime.hpp:93-98),
+:class:`RangeError` ~ ``std::range_error`` (nufi/cuda_kernel.cu:115-116), ``MemoryError`` ~ ``std::bad_alloc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .config import F0, n_nodes, n_quad, stride_t
+
+__all__ = ["CudaScheduler", "CudaError", "RangeError", "measure_fp64_peak"]
+
+
+class CudaError(RuntimeError):
+    """CUDA/cuFFT failure or no device (the reference throws nufi::cuda::exception)."""
+
+
+class RangeError(ValueError):
+    """Time step / index out of range (the reference throws std::range_error)."""
+
+
+def _raise(code: int, msg: str):
+    if code == _lib.ERR_RANGE:
+        raise RangeError(msg)
+    if code == _lib.ERR_ALLOC:
+        raise MemoryError(msg)
+    if code == _lib.ERR_ARG:
+        raise ValueError(msg)
+    raise CudaError(msg)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class CudaScheduler:
+    """``cuda_scheduler<double,4>`` for one GPU.
+
+    Parameters mirror the reference constructor (``cuda_scheduler(const config_t&)``); ``f0`` replaces the
+    compile-time choice of ``config_t::f0``; ``device=-1`` uses the current CUDA device.
+    """
+
+    def __init__(self, conf, f0: F0 | None = None, order: int = 4, device: int = -1):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        self.conf = conf
+        self.dim = conf.dim
+        self.order = order
+        self.f0 = f0 if f0 is not None else F0.default(conf.dim)
+        self.n_nodes = n_nodes(conf)
+        self.n_quad = n_quad(conf)
+        self.stride_t = stride_t(conf, order)
+        create = getattr(self._L, f"nufi_b200_create_{conf.dim}d")
+        rc = create(C.addressof(conf), order, C.addressof(self.f0), device, C.byref(self._h))
+        if rc != _lib.OK:
+            self._h = C.c_void_p()
+            _raise(rc, self._L.nufi_b200_last_error(None).decode())
+
+    # -- plumbing
+    def _ck(self, rc: int):
+        if rc != _lib.OK:
+            _raise(rc, self._L.nufi_b200_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.nufi_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- the reference scheduler's methods
+    def compute_rho(self, n: int, q_begin: int, q_end: int) -> None:
+        """Asynchronous partial rho over flat q in [q_begin, q_end) (cuda_scheduler.hpp:88-111)."""
+        self._ck(self._L.nufi_b200_compute_rho(self._h, n, q_begin, q_end))
+
+    def download_rho(self, rho: np.ndarray) -> None:
+        """Blocking; ``rho += partial`` (caller zeroes first, bin/test_nufi_gpu_3d.cpp:154-156)."""
+        assert rho.dtype == np.float64 and rho.flags.c_contiguous and rho.size == self.n_nodes
+        self._ck(self._L.nufi_b200_download_rho(self._h, _ptr(rho)))
+
+    def upload_phi(self, n: int, coeffs: np.ndarray) -> None:
+        """Copies level ``n`` out of the BASE array of the host history (cuda_kernel.cu:147-156)."""
+        assert coeffs.dtype == np.float64 and coeffs.flags.c_contiguous
+        if coeffs.size < (n + 1) * self.stride_t:
+            raise RangeError("host history holds fewer than n+1 levels")
+        self._ck(self._L.nufi_b200_upload_phi(self._h, n, _ptr(coeffs)))
+
+    def compute_metrics(self, n: int, q_begin: int, q_end: int) -> None:
+        self._ck(self._L.nufi_b200_compute_metrics(self._h, n, q_begin, q_end))
+
+    def download_metrics(self, metrics: np.ndarray) -> None:
+        assert metrics.dtype == np.float64 and metrics.size == 4
+        self._ck(self._L.nufi_b200_download_metrics(self._h, _ptr(metrics)))
+
+    # -- CPU-driver-shaped calls
+    def eval_rho(self, n: int, fetch: bool = True):
+        """The drivers' OpenMP sweep ``rho[l] = eval_rho(n, l, coeffs, conf)`` for all l (CPU convention)."""
+        rho = np.empty(self.n_nodes) if fetch else None
+        self._ck(self._L.nufi_b200_eval_rho_all(self._h, n, _ptr(rho) if fetch else None))
+        return rho
+
+    def solve_interpolate(self, n: int, rho: np.ndarray | None = None, want_energy: bool = True):
+        """``poisson.solve`` + ``interpolate`` into device level n; returns the electric energy."""
+        e = C.c_double(0.0)
+        if rho is not None:
+            rho = np.ascontiguousarray(rho, dtype=np.float64)
+            self._ck(self._L.nufi_b200_solve_interpolate_host(self._h, n, _ptr(rho), C.byref(e)))
+            return e.value
+        self._ck(self._L.nufi_b200_solve_interpolate(self._h, n, C.byref(e) if want_energy else None))
+        return e.value if want_energy else None
+
+    # -- fused path
+    def step(self, n: int) -> None:
+        """Backtrace + reduce + Poisson + interpolate + store level n, asynchronously, no host round trip."""
+        self._ck(self._L.nufi_b200_step(self._h, n))
+
+    def download_energy(self, n_begin: int, n_end: int) -> np.ndarray:
+        out = np.zeros(max(n_end - n_begin, 0))
+        self._ck(self._L.nufi_b200_download_energy(self._h, n_begin, n_end, _ptr(out)))
+        return out
+
+    def download_phi(self, n: int) -> np.ndarray:
+        out = np.empty(self.stride_t)
+        self._ck(self._L.nufi_b200_download_phi(self._h, n, _ptr(out)))
+        return out
+
+    def upload_history(self, coeffs: np.ndarray, n_levels: int) -> None:
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.float64).ravel()
+        for m in range(n_levels):
+            self.upload_phi(m, coeffs)
+
+    def sync(self) -> None:
+        self._ck(self._L.nufi_b200_sync(self._h))
+
+    # -- device plumbing (torch.distributed host layer)
+    def set_stream(self, cuda_stream: int | None) -> None:
+        self._ck(self._L.nufi_b200_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def rho_device_ptr(self) -> int:
+        p = C.c_void_p()
+        self._ck(self._L.nufi_b200_rho_device(self._h, C.byref(p)))
+        return p.value
+
+    def field_tail_device(self, n: int, d_rho_partial_sum: int) -> None:
+        self._ck(self._L.nufi_b200_field_tail_device(self._h, n, C.c_void_p(d_rho_partial_sum)))
+
+    # -- introspection
+    @property
+    def launches(self) -> int:
+        return int(self._L.nufi_b200_launch_count(self._h))
+
+    def last_backtrace_ms(self) -> float:
+        ms = C.c_float(0)
+        self._ck(self._L.nufi_b200_last_backtrace_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    @property
+    def last_variant(self) -> str:
+        return self._L.nufi_b200_last_variant(self._h).decode()
+
+    def set_variant(self, v: int) -> None:
+        self._ck(self._L.nufi_b200_set_variant(self._h, v))
+
+
+def measure_fp64_peak(device: int = -1) -> float:
+    """Register-only DFMA loop: measured FP64 peak of the device in TFLOP/s."""
+    L = _lib.load()
+    t = C.c_double(0)
+    rc = L.nufi_b200_measure_fp64_peak(device, C.byref(t))
+    if rc != _lib.OK:
+        _raise(rc, L.nufi_b200_last_error(None).decode())
+    return t.value

@@ -1,0 +1,147 @@
+"""GPU parity tests proper: libnufi_b200.so (through its C ABI) against the CPU oracle on the same inputs.
+
+Tolerances are the north star's: rho relative L-infinity <= 1e-10 per step on the SAME history
+(teacher-forced), electric-energy trace relative error <= 1e-8 over a free run."""
+import numpy as np
+import pytest
+
+from cases import CASES, conf1d, conf2d, conf3d, rel_linf
+from numericalflowiteration_b200 import CudaScheduler, F0, RangeError, n_quad, stride_t
+
+pytestmark = pytest.mark.gpu
+
+RHO_TOL = 1e-10
+ENERGY_TOL = 1e-8
+COEFF_TOL = 1e-11
+
+
+@pytest.fixture(scope="module")
+def histories(oracle):
+    """Free-running oracle histories (the reference CPU loop) for every case."""
+    out = {}
+    for name, (mk, f0) in CASES.items():
+        conf = mk()
+        n_lev = conf.Nt
+        coeffs, energy, _ = oracle.run(conf, f0, n_lev)
+        out[name] = (conf, f0, coeffs, energy)
+    return out
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("variant", [1, 2])
+def test_rho_teacher_forced(name, variant, histories, oracle):
+    conf, f0, coeffs, _ = histories[name]
+    with CudaScheduler(conf, f0) as s:
+        s.set_variant(variant)
+        s.upload_history(coeffs, conf.Nt)
+        for n in (0, 1, 2, 5, conf.Nt - 1, conf.Nt):
+            got = s.eval_rho(n)
+            want = oracle.rho(conf, f0, n, coeffs)
+            err = rel_linf(got, want)
+            assert err <= RHO_TOL, (name, variant, n, err, s.last_variant)
+
+
+@pytest.mark.parametrize("name", ["1d-two-stream", "2d-landau", "3d-landau"])
+def test_partial_ranges_accumulate(name, histories, oracle):
+    """compute_rho/download_rho keep the reference GPU convention: partial = -dV*sum f, download accumulates;
+    arbitrary [q_begin,q_end) cuts (ragged ends inside a node's velocity range) sum to the whole."""
+    conf, f0, coeffs, _ = histories[name]
+    nq = n_quad(conf)
+    rng = np.random.default_rng(7)
+    cuts = sorted(set([0, nq] + [int(c) for c in rng.integers(1, nq - 1, size=5)]))
+    n = conf.Nt // 2
+    with CudaScheduler(conf, f0) as s:
+        s.upload_history(coeffs, conf.Nt)
+        total = np.zeros(s.n_nodes)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            s.compute_rho(n, a, b)
+            part = np.zeros(s.n_nodes)
+            s.download_rho(part)
+            want = oracle.rho_partial(conf, f0, n, coeffs, a, b)
+            scale = np.max(np.abs(want))
+            assert np.max(np.abs(part - want)) <= 1e-12 * max(scale, 1e-300) + 1e-15, (name, a, b)
+            total += part
+        s.compute_rho(n, 5, 5)  # empty range -> zero partial
+        z = np.zeros(s.n_nodes)
+        s.download_rho(z)
+        assert not z.any()
+        want = oracle.rho(conf, f0, n, coeffs)
+        assert rel_linf(1.0 + total, want) <= RHO_TOL
+
+
+@pytest.mark.parametrize("name", ["1d-landau", "2d-landau", "3d-landau", "3d-bump"])
+def test_field_tail(name, histories, oracle):
+    """solve + interpolate on the device vs poisson.cpp / fields.hpp restated (and LSMR via oracle/_ref in
+    test_oracle_vs_ref): coefficients and electric energy."""
+    conf, f0, coeffs, _ = histories[name]
+    n = 3
+    rho = oracle.rho(conf, f0, n, coeffs)
+    phi, e_want = oracle.poisson(conf, rho)
+    level_want = oracle.interpolate(conf, phi)
+    with CudaScheduler(conf, f0) as s:
+        e_got = s.solve_interpolate(n, rho=rho)
+        level_got = s.download_phi(n)
+    assert abs(e_got - e_want) <= 1e-12 * abs(e_want)
+    assert rel_linf(level_got, level_want) <= COEFF_TOL
+
+
+@pytest.mark.parametrize("name", ["1d-two-stream", "1d-landau", "2d-landau", "3d-landau", "3d-bump"])
+def test_free_run_energy_trace(name, histories):
+    """The fused step() loop, no host round trip, against the reference CPU loop."""
+    conf, f0, coeffs, energy = histories[name]
+    with CudaScheduler(conf, f0) as s:
+        for n in range(conf.Nt):
+            s.step(n)
+        got = s.download_energy(0, conf.Nt)
+        last = s.download_phi(conf.Nt - 1)
+    rel = np.max(np.abs(got - energy) / np.abs(energy))
+    assert rel <= ENERGY_TOL, (name, rel)
+    st = stride_t(conf)
+    assert rel_linf(last, coeffs[(conf.Nt - 1) * st: conf.Nt * st]) <= 1e-8
+
+
+def test_upload_download_roundtrip_and_errors(histories):
+    conf, f0, coeffs, _ = histories["2d-landau"]
+    st = stride_t(conf)
+    with CudaScheduler(conf, f0) as s:
+        s.upload_phi(2, coeffs)
+        assert np.array_equal(s.download_phi(2), coeffs[2 * st:3 * st])
+        with pytest.raises(RangeError):
+            s.compute_rho(conf.Nt + 1, 0, 10)  # "Time-step out of range." (cuda_kernel.cu:115-116)
+        with pytest.raises(RangeError):
+            s.compute_rho(5, 0, 10)  # levels 0,1,3,4 never uploaded
+        with pytest.raises(RangeError):
+            s.compute_rho(0, 0, n_quad(conf) + 1)
+    with pytest.raises(ValueError):
+        CudaScheduler(conf, f0, order=5)
+    with pytest.raises(ValueError):
+        CudaScheduler(conf, F0(7))
+
+
+@pytest.mark.parametrize("name", ["1d-two-stream", "2d-landau", "3d-landau"])
+def test_metrics(name, histories, oracle):
+    conf, f0, coeffs, _ = histories[name]
+    nq = n_quad(conf)
+    n = conf.Nt - 1
+    with CudaScheduler(conf, f0) as s:
+        s.upload_history(coeffs, conf.Nt)
+        got = np.zeros(4)
+        for a, b in ((0, nq // 3), (nq // 3, nq)):
+            s.compute_metrics(n, a, b)
+            s.download_metrics(got)
+        s.compute_metrics(0, 0, nq)
+        got0 = np.zeros(4)
+        s.download_metrics(got0)
+    want = oracle.metrics(conf, f0, n, coeffs, 0, nq)
+    want0 = oracle.metrics(conf, f0, 0, coeffs, 0, nq)
+    assert np.max(np.abs(got - want) / np.abs(want)) <= 1e-11
+    assert np.max(np.abs(got0 - want0) / np.abs(want0)) <= 1e-11
+
+
+def test_run_to_run_deterministic(histories):
+    conf, f0, coeffs, _ = histories["2d-landau"]
+    with CudaScheduler(conf, f0) as s:
+        s.upload_history(coeffs, conf.Nt)
+        a = s.eval_rho(conf.Nt)
+        b = s.eval_rho(conf.Nt)
+    assert np.array_equal(a, b)
