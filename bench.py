@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py -- backtrace point-steps/s of the NuFI hot path on B200 (driver contract: see the task statement).
+
+A *step* is one NuFI time step at a fixed history depth n: trace every quadrature point back through the n stored
+levels, f0 at the foot, reduce into rho, Poisson + spline interpolation into level n -- all on the device, through
+the C ABI of libnufi_b200.so.  One step costs Nquad * n point-steps.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C1|C2|C3|C4|C5-16|C5-32] [--depth n]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1: one rank per GPU)
+    python bench.py --impl reference ...      the reference's own CPU eval_rho (oracle/_ref) on the host cores
+
+Only the cpu_baseline leg and --impl reference execute anything under oracle/ (as the measured CPU baseline and as
+the live parity check); the GPU numbers never touch it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_POINT_STEP = {1: 30.0, 2: 138.0, 3: 431.0}  # SURVEY.md section 8d / App. A.4 (algorithmic, FMA = 2)
+L2_FLUSH_BYTES = 256 << 20
+
+
+def make_workload(name: str, n_gpus: int):
+    """(conf, f0, depth n, description).  Weak scaling: the velocity quadrature grows with the GPU count so the
+    quadrature points per GPU stay fixed (BASELINE.json configs[4]: 'larger Nx and Nv quadrature')."""
+    from numericalflowiteration_b200 import Config1D, Config2D, Config3D, F0
+
+    g = max(n_gpus, 1)
+    if name in ("C1", "C2"):
+        conf = Config1D(Nu=512 * g)  # 256 x 512, dt = 1/16, Nt = 1600 (nufi/config.hpp:58-65)
+        f0 = F0(0, 0.01, 0.5) if name == "C1" else F0(1, 0.01, 0.5)
+        what = "1d1v weak Landau" if name == "C1" else "1d1v two-stream, long horizon"
+        return conf, f0, 800, f"{name}: {what} Nx=256 Nu={conf.Nu} dt=1/16 Nt=1600"
+    if name == "C3":
+        conf = Config2D(Nv=128 * g)  # 32^2 x 128^2, Nt = 800 (nufi/config.hpp:120-130)
+        return conf, F0(0, 0.05, 0.5), 100, f"C3: 2d2v weak Landau 32^2 x 128x{conf.Nv} dt=1/16 Nt=800"
+    L = 10 * math.pi
+    box = dict(x_max=L, y_max=L, z_max=L, u_min=-6, u_max=6, v_min=-6, v_max=6, w_min=-6, w_max=6)
+    if name == "C4":
+        conf = Config3D(Nw=8 * g, **box)  # 8^3 x 8^3, dt = 0.1, Nt = 50 (nufi/config.hpp:199-208)
+        return conf, F0(0, 0.001, 0.2), 50, f"C4: 3d3v weak Landau 8^3 x 8x8x{conf.Nw} dt=0.1 Nt=50"
+    if name.startswith("C5-"):
+        nx = int(name[3:])
+        conf = Config3D(Nx=nx, Ny=nx, Nz=nx, Nu=nx, Nv=nx, Nw=nx * g, **box)
+        return conf, F0(0, 0.001, 0.2), 25, f"{name}: 3d3v weak Landau {nx}^3 x {nx}x{nx}x{conf.Nw} dt=0.1 Nt=50"
+    raise SystemExit(f"unknown workload {name}")
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    BAD = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80}
+    NOTE = {"sw_power_cap": 0x4}
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.samples, self.reasons, self.sm_max, self.ok = [], set(), None, False
+        self.period = period_s
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.ok:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def reference_sweep_timer(conf, f0, n, coeffs, budget_s: float):
+    """Times the reference's own OpenMP rho sweep (oracle/_ref, -O3 AVX2+FMA build; falls back to the C port) on a
+    bounded sample of spatial nodes.  Returns (callable running one sample -> seconds, point-steps per sample,
+    description, kind, threads, rho of the sample nodes)."""
+    from oracle.oracle_py import Oracle, Reference
+    from numericalflowiteration_b200 import n_nodes, n_vel
+
+    if Reference.available("_fast"):
+        impl = Reference("_fast")
+    else:
+        impl = Oracle(fast=True)
+    nn, nv = n_nodes(conf), n_vel(conf)
+    threads = impl.threads()
+    # calibrate on a few nodes, then size the sample for the budget
+    l_cal = min(nn, max(threads, 8))
+    t0 = time.perf_counter()
+    impl.rho(conf, f0, n, coeffs, 0, l_cal)
+    t_cal = max(time.perf_counter() - t0, 1e-4)
+    per_node = t_cal / l_cal
+    l_n = int(min(nn, max(threads, budget_s / per_node)))
+    l_n = max(threads, (l_n // threads) * threads) if l_n < nn else nn
+    l_n = min(l_n, nn)
+    desc = (f"reference eval_rho sweep ({impl.kind}: {os.path.basename(impl.path)}, OpenMP {threads} threads) over spatial "
+            f"nodes [0,{l_n}) of {nn} at depth n={n}: {l_n * nv * n:.3e} point-steps per sample")
+    out = {}
+
+    def run():
+        t0 = time.perf_counter()
+        out["rho"] = impl.rho(conf, f0, n, coeffs, 0, l_n)
+        return time.perf_counter() - t0
+
+    return run, float(l_n) * nv * max(n, 1), desc, impl.kind, threads, l_n, out
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle_py import synthetic_history
+
+    conf, f0, depth, desc = make_workload(args.workload, args.gpus)
+    n = args.depth or depth
+    coeffs = synthetic_history(conf, n, seed=1234, amp=1e-2)
+    total = max(args.steps + args.warmup, 1)
+    budget = min(2.0, max(0.05, 90.0 / total))
+    run, psteps, sdesc, kind, threads, _, _ = reference_sweep_timer(conf, f0, n, coeffs, budget)
+    for _ in range(args.warmup):
+        run()
+    times = [run() for _ in range(args.steps)]
+    t = float(np.sum(times))
+    value = psteps * args.steps / t
+    line = {
+        "impl": "reference", "metric": "backtrace point-steps/sec", "value": value, "unit": "point-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "depth_n": n, "history": "synthetic smooth sine potentials (numpy), seed 1234"},
+        "cpu_baseline": {"value": value, "unit": "point-steps/s", "cores": threads, "kind": kind, "sample": sdesc},
+        "e2e": {"value": value, "unit": "point-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class GpuRunner:
+    """One rank's scheduler + (for N > 1) the NCCL all-reduce of the partial rho."""
+
+    def __init__(self, conf, f0, rank, world, torch, dist):
+        from numericalflowiteration_b200 import CudaScheduler, partition
+
+        self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
+        self.s = CudaScheduler(conf, f0, device=torch.cuda.current_device())
+        self.stream = torch.cuda.Stream()
+        self.s.set_stream(self.stream.cuda_stream)
+        self.q0, self.q1 = partition(self.s.n_quad, world, rank)
+        if world > 1:
+            from numericalflowiteration_b200.distributed import _alias_device_f64
+
+            self.rho_t = _alias_device_f64(torch, self.s.rho_device_ptr(), self.s.n_nodes)
+
+    def step(self, n):
+        """Fused step, no host round trip.  N > 1: local shard -> NCCL all-reduce (in place, device) -> replicated tail."""
+        if self.world == 1:
+            self.s.step(n)
+        else:
+            self.s.compute_rho(n, self.q0, self.q1)
+            with self.torch.cuda.stream(self.stream):
+                self.dist.all_reduce(self.rho_t, op=self.dist.ReduceOp.SUM)
+            self.s.field_tail_device(n, self.rho_t.data_ptr())
+
+
+def measure_gpu(runner, n, steps, warmup, flush, torch, dist, sampler=None):
+    """Event-timed fused steps at depth n with an (untimed) L2 flush between them.  Returns dict."""
+    s, st = runner.s, runner.stream
+    for _ in range(warmup):
+        runner.step(n)
+    st.synchronize()
+    if runner.world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    s.backtrace_time(reset=True)
+    l0 = s.launches
+    ctx = sampler if sampler is not None else _Null()
+    with ctx:
+        for a, b in ev:
+            with torch.cuda.stream(st):
+                flush.fill_(1.0)  # L2 flush, untimed
+            a.record(st)
+            runner.step(n)
+            b.record(st)
+        st.synchronize()
+        if runner.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    launches = s.launches - l0
+    bt_total, bt_count = s.backtrace_time(reset=True)  # CUDA event pair around every backtrace launch, same stream
+    t_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    if runner.world > 1:
+        tt = torch.tensor([t_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_ms = float(tt.item())
+    return {"t_ms": t_ms, "bt_ms": bt_total / max(bt_count, 1), "launches": int(launches)}
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def measure_e2e(runner, n, steps, warmup, coeffs_host, torch, dist):
+    """The reference GPU driver's per-step call sequence (bin/test_nufi_gpu_3d.cpp:154-162) through the C ABI with HOST
+    buffers: upload_phi(n-1) [H2D] -> compute_rho(n, q-range) -> download_rho [D2H] -> (N > 1: all-reduce) ->
+    solve + interpolate from the host rho [H2D] -> energy [D2H]."""
+    s = runner.s
+    rho = np.zeros(s.n_nodes)
+    h2d = s.stride_t * 8 + s.n_nodes * 8
+    d2h = s.n_nodes * 8 + 8
+
+    def one():
+        if n > 0:
+            s.upload_phi(n - 1, coeffs_host)
+        rho[:] = 0.0
+        s.compute_rho(n, runner.q0, runner.q1)
+        s.download_rho(rho)
+        if runner.world > 1:
+            t = torch.from_numpy(rho).cuda()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            rho[:] = t.cpu().numpy()
+        return s.solve_interpolate(n, rho=1.0 + rho)
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    if runner.world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e = one()
+    torch.cuda.synchronize()
+    if runner.world > 1:
+        dist.barrier()
+    t = time.perf_counter() - t0
+    if runner.world > 1:
+        tt = torch.tensor([t], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt.item())
+    return t, h2d, d2h, e
+
+
+def free_run(runner, n_levels):
+    """Build the history on the device: fused steps 0 .. n_levels-1 (no host round trip)."""
+    for m in range(n_levels):
+        runner.step(m)
+    runner.stream.synchronize()
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world != max(args.gpus, 1):
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+
+    from numericalflowiteration_b200 import measure_fp64_peak, n_quad, stride_t
+
+    conf, f0, depth, desc = make_workload(args.workload, world)
+    n = args.depth or depth
+    dim = conf.dim
+    runner = GpuRunner(conf, f0, rank, world, torch, dist)
+    s = runner.s
+    nq = n_quad(conf)
+    flush = torch.empty(L2_FLUSH_BYTES // 8, dtype=torch.float64, device="cuda")
+
+    t0 = time.perf_counter()
+    free_run(runner, n)  # levels 0..n-1 on the device
+    t_hist = time.perf_counter() - t0
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    m = measure_gpu(runner, n, args.steps, args.warmup, flush, torch, dist, sampler)
+    psteps = float(nq) * n  # whole job, all ranks
+    value = psteps * args.steps / (m["t_ms"] * 1e-3)
+    variant = s.last_variant
+
+    # host copy of the history (for the e2e leg's upload_phi and for the CPU baseline / live parity check)
+    st_ = stride_t(conf)
+    coeffs_host = np.zeros((n + 1) * st_)
+    for lvl in range(n):
+        coeffs_host[lvl * st_:(lvl + 1) * st_] = s.download_phi(lvl)
+    e2e_steps = max(3, min(args.steps, 50))
+    t_e2e, h2d, d2h, _ = measure_e2e(runner, n, e2e_steps, min(args.warmup, 3), coeffs_host, torch, dist)
+    e2e_value = psteps * e2e_steps / t_e2e
+
+    line = None
+    if rank == 0:
+        peak_tf = measure_fp64_peak(local)
+        # this rank's backtrace kernel: its share of the point-steps / its average launch duration
+        my_psteps = float(runner.q1 - runner.q0) * n
+        achieved_tf = my_psteps * FLOP_PER_POINT_STEP[dim] / (m["bt_ms"] * 1e-3) / 1e12
+        hist_bytes = float(n) * s.stride_t * 8 + 2 * 8 * s.n_nodes
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        roofline = {
+            "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+            "traffic": None,
+            "kernel": f"backtrace_kernel<{dim}d> [{variant}]", "kernel_ms": m["bt_ms"],
+            "kernel_share_of_step": m["bt_ms"] * args.steps / m["t_ms"] if world == 1 else None,
+            "flop_per_point_step": FLOP_PER_POINT_STEP[dim],
+            "peak_source": "measured live: register-only DFMA loop (nufi_b200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+            "hbm": {"achieved": hist_bytes / (m["bt_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": hist_bytes / (m["bt_ms"] * 1e-3) / 1e9 / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                    "note": "algorithmic bytes = n*stride_t*8 (history read once) + 2*8*Nnodes; shown to document the path is not HBM-bound"},
+        }
+        cpu = None
+        parity = None
+        if world == 1 and not args.no_cpu:
+            run, cpu_psteps, sdesc, kind, threads, l_n, out = reference_sweep_timer(conf, f0, n, coeffs_host, args.cpu_budget)
+            run()  # warm
+            t_cpu = run()
+            cpu = {"value": cpu_psteps / t_cpu, "unit": "point-steps/s", "cores": threads, "kind": kind, "sample": sdesc,
+                   "seconds": t_cpu}
+            got = s.eval_rho(n)
+            want = out["rho"][:l_n]
+            parity = {"rho_rel_linf_vs_cpu_reference": float(np.max(np.abs(got[:l_n] - want)) / np.max(np.abs(want))),
+                      "nodes_checked": int(l_n), "tolerance": 1e-10}
+        line = {
+            "metric": "backtrace point-steps/sec", "value": value, "unit": "point-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["t_ms"] / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "depth_n": n, "point_steps_per_step": psteps, "n_quad": nq,
+                       "history": f"built on the device by {n} free-running fused steps ({t_hist:.2f} s)",
+                       "l2": "flushed between timed steps (256 MiB fill, untimed; steps timed individually with CUDA events)",
+                       "parallelism": f"quadrature points sharded over {world} GPU(s), NCCL all-reduce of rho" if world > 1 else "1 GPU"},
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+            "e2e": {"value": e2e_value, "unit": "point-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps,
+                    "path": "upload_phi(n-1) -> compute_rho -> download_rho -> solve_interpolate_host, host buffers, wall clock"},
+            "gpu_launches": m["launches"], "clocks": sampler.summary() if sampler else None,
+            "s_per_time_step": m["t_ms"] / args.steps * 1e-3,
+        }
+
+    if world == 1 and args.extras and rank == 0:
+        extras = []
+        del runner, s
+        for name in [w for w in ("C1", "C3", "C4", "C5-16", "C5-32") if w != args.workload]:
+            try:
+                c2, f2, d2, desc2 = make_workload(name, 1)
+                r2 = GpuRunner(c2, f2, 0, 1, torch, dist)
+                free_run(r2, d2)
+                k = 5 if c2.dim == 3 and c2.Nx >= 32 else 20
+                m2 = measure_gpu(r2, d2, k, 3, flush, torch, dist)
+                ps = float(n_quad(c2)) * d2
+                tf = ps * FLOP_PER_POINT_STEP[c2.dim] / (m2["bt_ms"] * 1e-3) / 1e12
+                extras.append({"workload": desc2, "depth_n": d2, "point_steps_per_s": ps * k / (m2["t_ms"] * 1e-3),
+                               "ms_per_step": m2["t_ms"] / k, "kernel_ms": m2["bt_ms"], "variant": r2.s.last_variant,
+                               "fp64_tflops": tf, "fp64_frac": tf / line["roofline"]["peak"]})
+                r2.s.close()
+            except Exception as e:  # noqa: BLE001
+                extras.append({"workload": name, "error": repr(e)})
+        line["other_workloads"] = extras
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--depth", type=int, default=0, help="history depth n of the timed step (default: per workload)")
+    ap.add_argument("--cpu-budget", type=float, default=3.0, help="seconds of wall time for the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", dest="extras", action="store_false")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -152,6 +152,9 @@ int nufi_b200_field_tail_device(nufi_b200_handle *h, size_t n, const double *d_r
 uint64_t nufi_b200_launch_count(const nufi_b200_handle *h);
 /* GPU time in ms of the most recent backtrace kernel (CUDA events on the launching stream); blocking */
 int nufi_b200_last_backtrace_ms(nufi_b200_handle *h, float *ms);
+/* accumulated GPU time and number of backtrace kernel launches since the last reset (every launch is bracketed by a
+ * CUDA event pair on its stream; the pairs are read back lazily, so this call blocks, the launches do not) */
+int nufi_b200_backtrace_time(nufi_b200_handle *h, double *total_ms, uint64_t *count, int reset);
 /* which kernel variant the last compute_rho used: writes a short static string ("smem-tma", "global") */
 const char *nufi_b200_last_variant(const nufi_b200_handle *h);
 /* force a variant for A/B tests: 0 auto, 1 global-memory path, 2 shared-memory staged path */

@@ -18,6 +18,44 @@ int fail(Handle *h, int code, const std::string &msg)
     return code;
 }
 
+// ---- event ring: one (start, stop) pair per backtrace launch, read back lazily so timing never stalls the stream
+static int ev_fold_oldest(Handle *h)
+{
+    const size_t oldest = (h->ev_head + kEvRingPairs - h->ev_pending) % kEvRingPairs;
+    NUFI_CUDA_CHECK(h, cudaEventSynchronize(h->ev_ring[2 * oldest + 1]));
+    float ms = 0;
+    NUFI_CUDA_CHECK(h, cudaEventElapsedTime(&ms, h->ev_ring[2 * oldest], h->ev_ring[2 * oldest + 1]));
+    h->bt_ms_total += ms;
+    h->bt_ms_last = ms;
+    h->bt_count += 1;
+    h->ev_pending -= 1;
+    return NUFI_B200_OK;
+}
+
+int ev_acquire(Handle *h, cudaEvent_t *start, cudaEvent_t *stop)
+{
+    if (h->ev_ring.empty()) h->ev_ring.assign(2 * kEvRingPairs, nullptr);
+    if (h->ev_pending == kEvRingPairs) { // full: fold the oldest pair first
+        int rc = ev_fold_oldest(h);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < 2; ++i)
+        if (!h->ev_ring[2 * h->ev_head + i]) NUFI_CUDA_CHECK(h, cudaEventCreate(&h->ev_ring[2 * h->ev_head + i]));
+    *start = h->ev_ring[2 * h->ev_head];
+    *stop = h->ev_ring[2 * h->ev_head + 1];
+    h->ev_head = (h->ev_head + 1) % kEvRingPairs;
+    return NUFI_B200_OK;
+}
+
+int ev_drain(Handle *h)
+{
+    while (h->ev_pending > 0) {
+        int rc = ev_fold_oldest(h);
+        if (rc) return rc;
+    }
+    return NUFI_B200_OK;
+}
+
 namespace
 {
 
@@ -30,8 +68,8 @@ void free_all(Handle *h)
     cudaFree(h->d_rho_partial); cudaFree(h->d_rho_full); cudaFree(h->d_partials);
     cudaFree(h->d_metrics); cudaFree(h->d_mpartials); cudaFree(h->d_energy); cudaFree(h->d_stage);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
-    if (h->ev0) cudaEventDestroy(h->ev0);
-    if (h->ev1) cudaEventDestroy(h->ev1);
+    for (cudaEvent_t e : h->ev_ring)
+        if (e) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -97,8 +135,6 @@ int create_common(const nufi_b200_config3d &c, int dim, int order, const nufi_b2
     h->smem_optin = prop.sharedMemPerBlockOptin;
     CREATE_CHECK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
-    CREATE_CHECK(cudaEventCreate(&h->ev0));
-    CREATE_CHECK(cudaEventCreate(&h->ev1));
     const size_t hist_bytes = (c.Nt + 1) * h->level_stride * sizeof(double);
     CREATE_CHECK(cudaMalloc(&h->d_hist, hist_bytes));
     CREATE_CHECK(cudaMemsetAsync(h->d_hist, 0, hist_bytes, h->stream));
@@ -346,8 +382,11 @@ int nufi_b200_set_stream(nufi_b200_handle *h, void *cuda_stream)
 {
     ENTER(h);
     NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    {
+        int rc = ev_drain(hh);
+        if (rc) return rc;
+    }
     hh->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : hh->own_stream;
-    hh->ev_valid = false;
     return NUFI_B200_OK;
 }
 
@@ -375,9 +414,24 @@ int nufi_b200_last_backtrace_ms(nufi_b200_handle *h, float *ms)
 {
     ENTER(h);
     if (!ms) return fail(hh, NUFI_B200_ERR_ARG, "ms is NULL");
-    if (!hh->ev_valid) return fail(hh, NUFI_B200_ERR_RANGE, "no backtrace kernel has been launched on this stream yet");
-    NUFI_CUDA_CHECK(hh, cudaEventSynchronize(hh->ev1));
-    NUFI_CUDA_CHECK(hh, cudaEventElapsedTime(ms, hh->ev0, hh->ev1));
+    int rc = ev_drain(hh);
+    if (rc) return rc;
+    if (hh->bt_count == 0) return fail(hh, NUFI_B200_ERR_RANGE, "no backtrace kernel has been launched yet");
+    *ms = static_cast<float>(hh->bt_ms_last);
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_backtrace_time(nufi_b200_handle *h, double *total_ms, uint64_t *count, int reset)
+{
+    ENTER(h);
+    int rc = ev_drain(hh);
+    if (rc) return rc;
+    if (total_ms) *total_ms = hh->bt_ms_total;
+    if (count) *count = hh->bt_count;
+    if (reset) {
+        hh->bt_ms_total = 0;
+        hh->bt_count = 0;
+    }
     return NUFI_B200_OK;
 }
 

@@ -579,14 +579,19 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
         NUFI_CUDA_CHECK(h, cudaMemsetAsync(h->d_mpartials, 0, sizeof(double) * 4 * grid, h->stream));
     }
 
-    NUFI_CUDA_CHECK(h, cudaEventRecord(h->ev0, h->stream));
+    cudaEvent_t ev_start, ev_stop;
+    {
+        int rc = ev_acquire(h, &ev_start, &ev_stop);
+        if (rc) return rc;
+    }
+    NUFI_CUDA_CHECK(h, cudaEventRecord(ev_start, h->stream));
     cudaError_t e;
     if (h->dim == 1) e = launch_dim<1>(P, ilp, staged, grid, threads, smem_bytes, h->stream);
     else if (h->dim == 2) e = launch_dim<2>(P, ilp, staged, grid, threads, smem_bytes, h->stream);
     else e = launch_dim<3>(P, ilp, staged, grid, threads, smem_bytes, h->stream);
     NUFI_CUDA_CHECK(h, e);
-    NUFI_CUDA_CHECK(h, cudaEventRecord(h->ev1, h->stream));
-    h->ev_valid = true;
+    NUFI_CUDA_CHECK(h, cudaEventRecord(ev_stop, h->stream));
+    h->ev_pending += 1;
     h->launches += 1;
     h->last_variant = staged ? (ilp == 2 ? "smem-tma/ilp2" : "smem-tma/ilp1") : (ilp == 2 ? "global/ilp2" : "global/ilp1");
 

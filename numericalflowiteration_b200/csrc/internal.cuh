@@ -88,8 +88,11 @@ struct Handle
     size_t n_spec = 0;
     // streams / events
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_valid = false;
+    // backtrace kernel timing: ring of CUDA event pairs on the launching stream, drained lazily
+    std::vector<cudaEvent_t> ev_ring; // 2 per launch: [start, stop]
+    size_t ev_head = 0, ev_pending = 0; // next slot (in pairs), pairs recorded but not yet read
+    double bt_ms_total = 0, bt_ms_last = 0;
+    uint64_t bt_count = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
     int variant_force = 0;
@@ -109,6 +112,10 @@ int fail(Handle *h, int code, const std::string &msg);
                                          " [" #expr "]");                                             \
     } while (0)
 
+// api.cu: event ring
+constexpr size_t kEvRingPairs = 256;
+int ev_acquire(Handle *h, cudaEvent_t *start, cudaEvent_t *stop); // next pair (drains the oldest when the ring is full)
+int ev_drain(Handle *h);                                          // blocking: fold all pending pairs into the totals
 // backtrace.cu
 int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool metrics);
 // tail.cu

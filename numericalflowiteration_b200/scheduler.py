@@ -175,6 +175,12 @@ class CudaScheduler:
         self._ck(self._L.nufi_b200_last_backtrace_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def backtrace_time(self, reset: bool = False) -> tuple[float, int]:
+        """(total GPU ms, launches) of the backtrace kernel since the last reset (blocking)."""
+        ms, cnt = C.c_double(0), C.c_uint64(0)
+        self._ck(self._L.nufi_b200_backtrace_time(self._h, C.byref(ms), C.byref(cnt), int(reset)))
+        return ms.value, int(cnt.value)
+
     @property
     def last_variant(self) -> str:
         return self._L.nufi_b200_last_variant(self._h).decode()

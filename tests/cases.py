@@ -41,3 +41,18 @@ def rel_linf(a, b):
     import numpy as np
 
     return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(np.asarray(b))))
+
+
+def load_golden(name):
+    """A committed reference fixture (tests/golden/<name>.npz, made by tests/golden/make_golden.py)."""
+    import os
+
+    import numpy as np
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    mk, f0 = CASES[name]
+    conf = mk()
+    for k, v in zip(g["conf_names"], g["conf_values"]):  # the fixture's config must be the case's config
+        assert float(getattr(conf, str(k))) == float(v), (name, k)
+    assert int(g["f0_kind"]) == f0.kind and list(g["f0_p"]) == list(f0.p)
+    return conf, f0, g

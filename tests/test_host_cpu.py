@@ -1,0 +1,150 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls -- there is no GPU here and no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from cases import conf2d
+from numericalflowiteration_b200 import (Config1D, Config2D, Config3D, CudaError, CudaScheduler, F0, _lib, n_nodes, n_quad,
+                                         partition, stride_t)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "nufi_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(nufi_b200_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations found"
+    assert sorted(_lib.SYMBOLS) == declared
+    L = _lib.load()
+    for s in declared:
+        assert hasattr(L, s), s
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (nufi_b200_\w+)", nm))
+    assert exported == set(declared)
+    assert b"sm_100a" in L.nufi_b200_version()
+
+
+def test_library_does_not_link_the_oracle():
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "oracle" not in out and "nufi_ref" not in out
+    nm = subprocess.run(["nm", "-D", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "orc_" not in nm and "ref_rho" not in nm
+
+
+def test_config_struct_layout_matches_header():
+    """ctypes mirrors == the C structs of include/nufi_b200.h (compiled with gcc) == config_t<double> layout."""
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "nufi_b200.h"
+int main(void){
+ printf("%zu %zu %zu %zu\n", sizeof(nufi_b200_config1d), offsetof(nufi_b200_config1d, dt), offsetof(nufi_b200_config1d, du), sizeof(nufi_b200_f0));
+ printf("%zu %zu %zu\n", sizeof(nufi_b200_config2d), offsetof(nufi_b200_config2d, dt), offsetof(nufi_b200_config2d, dv));
+ printf("%zu %zu %zu\n", sizeof(nufi_b200_config3d), offsetof(nufi_b200_config3d, dt), offsetof(nufi_b200_config3d, dw));
+ return 0; }'''
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")], check=True)
+        out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()
+    got = [int(x) for x in out]
+    want = [C.sizeof(Config1D), Config1D.dt.offset, Config1D.du.offset, C.sizeof(F0),
+            C.sizeof(Config2D), Config2D.dt.offset, Config2D.dv.offset,
+            C.sizeof(Config3D), Config3D.dt.offset, Config3D.dw.offset]
+    assert got == want
+    assert C.sizeof(Config1D) == 13 * 8 and C.sizeof(Config3D) == 35 * 8
+
+
+def test_sizes():
+    c1, c2, c3 = Config1D(), Config2D(), Config3D()
+    assert (stride_t(c1), stride_t(c2), stride_t(c3)) == (259, 1225, 1331)
+    assert (n_quad(c1), n_quad(c2), n_quad(c3)) == (131072, 16777216, 262144)
+    assert (n_nodes(c1), n_nodes(c2), n_nodes(c3)) == (256, 1024, 512)
+    assert (c1.Nt, c2.Nt, c3.Nt) == (1600, 800, 50)
+
+
+def test_partition_is_the_reference_rule():
+    """nufi/cuda_scheduler.hpp:88-111 / bin/test_nufi_gpu_3d.cpp:80-105: contiguous, first `rem` parts one longer."""
+    for total, parts in ((10, 3), (262144, 8), (7, 8), (0, 4), (131072, 5)):
+        edges = [partition(total, parts, p) for p in range(parts)]
+        assert edges[0][0] == 0 and edges[-1][1] == total
+        for (a, b), (c, d) in zip(edges[:-1], edges[1:]):
+            assert b == c
+        sizes = [b - a for a, b in edges]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    assert partition(10, 3, 1, begin=100) == (104, 107)
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_fails_loudly():
+    with pytest.raises(CudaError) as e:
+        CudaScheduler(conf2d(), F0(0, 0.05, 0.5))
+    assert "no CPU fallback" in str(e.value)
+    from numericalflowiteration_b200 import measure_fp64_peak
+
+    with pytest.raises(CudaError):
+        measure_fp64_peak()
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    with pytest.raises(ValueError):
+        CudaScheduler(conf2d(), F0(0, 0.05, 0.5), order=3)
+    with pytest.raises(ValueError):
+        CudaScheduler(conf2d(Nx=2), F0(0, 0.05, 0.5))
+
+
+_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.environ["NUFI_ROOT"]); sys.path.insert(0, os.path.join(os.environ["NUFI_ROOT"], "tests"))
+from cases import CASES
+from numericalflowiteration_b200 import n_quad, partition
+from numericalflowiteration_b200.distributed import host_allreduce_partials
+from oracle.oracle_py import Oracle
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+mk, f0 = CASES["2d-landau"]
+conf = mk()
+orc = Oracle()
+coeffs, _, _ = orc.run(conf, f0, 6)
+lo, hi = partition(n_quad(conf), world, rank)
+part = orc.rho_partial(conf, f0, 6, coeffs, lo, hi)     # stands in for the device work of this rank's shard
+total = host_allreduce_partials(dist, part)
+want = orc.rho(conf, f0, 6, coeffs)
+err = float(np.max(np.abs(1 + total - want)) / np.max(np.abs(want)))
+assert err <= 1e-13, err
+# every rank must hold the identical reduced vector (the replicated field tail depends on it)
+g = [None] * world
+dist.all_gather_object(g, total.tobytes())
+assert all(x == g[0] for x in g)
+print(f"rank {rank}/{world} q=[{lo},{hi}) err={err:.1e}")
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_rho_world_size_2_gloo(tmp_path):
+    """N > 1 host logic on CPU: reference partition of the flat q range per rank, all-reduce (gloo) of the partial rho,
+    identical result on every rank.  The oracle stands in for each rank's device work."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, NUFI_ROOT=ROOT, OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29517", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rank 0/2" in r.stdout and "rank 1/2" in r.stdout
