@@ -159,6 +159,10 @@ int nufi_b200_backtrace_time(nufi_b200_handle *h, double *total_ms, uint64_t *co
 const char *nufi_b200_last_variant(const nufi_b200_handle *h);
 /* force a variant for A/B tests: 0 auto, 1 global-memory path, 2 shared-memory staged path */
 int nufi_b200_set_variant(nufi_b200_handle *h, int variant);
+/* field-tail implementation: 0 auto (fused single-CTA kernel for grids up to 4096 nodes, cuFFT otherwise),
+ * 1 cuFFT D2Z + symbol + Z2D + expand, 2 fused single-CTA kernel */
+int nufi_b200_set_tail_variant(nufi_b200_handle *h, int variant);
+const char *nufi_b200_last_tail_variant(const nufi_b200_handle *h);
 /* register-only DFMA loop on `device`: measured FP64 peak in TFLOP/s (FMA = 2 flop) */
 int nufi_b200_measure_fp64_peak(int device, double *tflops);
 const char *nufi_b200_version(void);

@@ -19,7 +19,7 @@ SYMBOLS = [
     "nufi_b200_solve_interpolate_host", "nufi_b200_step", "nufi_b200_download_energy", "nufi_b200_download_phi",
     "nufi_b200_sync", "nufi_b200_set_stream", "nufi_b200_rho_device", "nufi_b200_field_tail_device",
     "nufi_b200_launch_count", "nufi_b200_last_backtrace_ms", "nufi_b200_backtrace_time", "nufi_b200_last_variant", "nufi_b200_set_variant",
-    "nufi_b200_measure_fp64_peak", "nufi_b200_version",
+    "nufi_b200_set_tail_variant", "nufi_b200_last_tail_variant", "nufi_b200_measure_fp64_peak", "nufi_b200_version",
 ]
 
 _lib = None
@@ -57,7 +57,7 @@ def load() -> C.CDLL:
         "download_energy": [vp, sz, sz, vp], "download_phi": [vp, sz, vp], "sync": [vp], "set_stream": [vp, vp],
         "rho_device": [vp, C.POINTER(vp)], "field_tail_device": [vp, sz, vp], "last_backtrace_ms": [vp, C.POINTER(C.c_float)],
         "set_variant": [vp, i], "measure_fp64_peak": [i, dp],
-        "backtrace_time": [vp, dp, C.POINTER(C.c_uint64), i],
+        "backtrace_time": [vp, dp, C.POINTER(C.c_uint64), i], "set_tail_variant": [vp, i],
     }.items():
         f = getattr(L, "nufi_b200_" + name)
         f.argtypes = args
@@ -66,6 +66,8 @@ def load() -> C.CDLL:
     L.nufi_b200_launch_count.restype = C.c_uint64
     L.nufi_b200_last_variant.argtypes = [vp]
     L.nufi_b200_last_variant.restype = C.c_char_p
+    L.nufi_b200_last_tail_variant.argtypes = [vp]
+    L.nufi_b200_last_tail_variant.restype = C.c_char_p
     L.nufi_b200_version.restype = C.c_char_p
     _lib = L
     return L

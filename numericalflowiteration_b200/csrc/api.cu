@@ -104,10 +104,9 @@ int create_common(const nufi_b200_config3d &c, int dim, int order, const nufi_b2
     h->stride_t = (c.Nx + 3) * (dim >= 2 ? c.Ny + 3 : 1) * (dim >= 3 ? c.Nz + 3 : 1);
     // device level format
     if (dim == 1) {
-        h->Nxp = static_cast<int>((c.Nx + 1) & ~size_t(1));
-        h->level_stride = 3 * static_cast<size_t>(h->Nxp);
+        h->level_stride = (3 * c.Nx + 1) & ~size_t(1); // per-cell quadratics [p0 p1 p2] (tail.cu), 16-byte multiple
         h->raw_stride = (c.Nx + 3 + 1) & ~size_t(1);
-        h->sx = h->Nxp; h->sxy = 0;
+        h->sx = 0; h->sxy = 0;
     } else {
         h->sx = static_cast<int>(c.Nx + 3);
         h->sxy = h->sx * static_cast<int>(c.Ny + 3);
@@ -341,9 +340,9 @@ int nufi_b200_step(nufi_b200_handle *h, size_t n)
     if (n > hh->Nt) return fail(hh, NUFI_B200_ERR_RANGE, "Time-step out of range.");
     int rc = check_levels(hh, n, "step");
     if (rc) return rc;
-    rc = launch_backtrace(hh, n, 0, hh->n_nodes * hh->n_vel, false);
+    rc = launch_backtrace(hh, n, 0, hh->n_nodes * hh->n_vel, false, /*defer_finish=*/true);
     if (rc) return rc;
-    return tail_run(hh, n, hh->d_rho_full);
+    return tail_run(hh, n, nullptr);
 }
 
 int nufi_b200_download_energy(nufi_b200_handle *h, size_t n_begin, size_t n_end, double *energies)
@@ -445,6 +444,17 @@ int nufi_b200_set_variant(nufi_b200_handle *h, int variant)
     hh->variant_force = variant;
     return NUFI_B200_OK;
 }
+
+int nufi_b200_set_tail_variant(nufi_b200_handle *h, int variant)
+{
+    Handle *hh = H(h);
+    if (!hh) return fail(nullptr, NUFI_B200_ERR_ARG, "handle is NULL");
+    if (variant < 0 || variant > 2) return fail(hh, NUFI_B200_ERR_ARG, "tail variant must be 0 (auto), 1 (cuFFT) or 2 (fused single CTA)");
+    hh->tail_force = variant;
+    return NUFI_B200_OK;
+}
+
+const char *nufi_b200_last_tail_variant(const nufi_b200_handle *h) { return h ? H(h)->last_tail : "none"; }
 
 int nufi_b200_measure_fp64_peak(int device, double *tflops) { return measure_fp64_peak(device, tflops); }
 

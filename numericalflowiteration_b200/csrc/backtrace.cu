@@ -4,22 +4,29 @@
 // (cuda_eval_metrics), i.e. the device flavour of nufi/rho.hpp eval_ftilda / eval_f / eval_rho with
 // nufi/fields.hpp eval and nufi/splines.hpp inlined.  Written from scratch for sm_100a:
 //
-//  * Work layout.  A warp-task is 32 consecutive spatial nodes (x fastest) sharing ONE velocity node, so the
-//    lanes of a warp drift rigidly and read neighbouring coefficients (conflict-free, coalesced) for the
-//    whole history, instead of the reference's "velocity fastest" layout whose lanes fan out and all hit one
-//    rho address with atomics.  Each thread owns a fixed node and sums f over its velocities in registers;
-//    per-(CTA,warp,tile) partial sums go to a slot array that a second tiny kernel adds in a fixed order:
-//    no atomics, run-to-run deterministic.
-//  * History access.  Persistent CTAs (one per SM).  Staged variant: a producer warp streams level after
-//    level from the HBM/L2-resident history into a shared-memory ring with cp.async.bulk (TMA bulk copy,
-//    SASS UBLKCP) + mbarrier full/empty pairs; consumer warps never wait on global memory.  Global variant
-//    (levels too big for shared memory, large 3d): read-only loads served by L1/L2.
-//  * Arithmetic.  Position per dimension = (cell k, centred offset tau); floor() and the float->int
-//    conversion (quarter-rate pipes) are replaced by the 1.5*2^52 rounding trick on the FP64 pipe.  1d levels
-//    are stored as per-cell quadratics of dt*E (3 doubles/cell, see tail.cu) so a 1d point-step is 7 FP64
-//    instructions; 2d/3d use the cubic B-spline window (16/64 doubles) with value and derivative bases
-//    computed once per dimension and shared between the field components.
+//  * Work layout.  A warp-unit is 32 consecutive spatial nodes (x fastest, a "tile") sharing ILP consecutive
+//    velocity nodes, so the lanes of a warp drift rigidly and read neighbouring coefficients (conflict-free)
+//    for the whole history -- instead of the reference's "velocity fastest" layout whose lanes fan out and all
+//    hit one rho address with atomics.  A CTA-round is W warp-units of the SAME tile; persistent CTAs (one per
+//    SM) take contiguous runs of CTA-rounds.  Each thread sums f of its node over its velocities in registers;
+//    when the CTA's tile changes the consumer warps combine their sums through shared memory in a fixed order
+//    and write ONE slot per (CTA, tile); a small kernel adds the slots of a tile in a fixed order.  No atomics:
+//    results are run-to-run deterministic.
+//  * History access.  Staged variant: a producer warp streams the history newest -> oldest from the HBM/L2-
+//    resident ring into a shared-memory ring of stages with cp.async.bulk (TMA bulk copy, SASS UBLKCP) +
+//    mbarrier full/empty pairs; a stage holds a CHUNK of several consecutive levels so barrier traffic and loop
+//    bookkeeping are amortised over the chunk.  Global variant (levels too big for shared memory, large 3d):
+//    read-only loads served by L1/L2.
+//  * Arithmetic.  Position per dimension = (cell k, centred offset tau in [-1/2,1/2]); floor() and the
+//    float->int conversion (quarter-rate pipes) are replaced by the 1.5*2^52 rounding trick on the FP64 pipe.
+//    The regular full-kick step is the only thing in the inner loop: eval_f's initial half kick and the final
+//    half kick on level 0 are peeled.  1d levels are stored as per-cell quadratics of dt*E (3 doubles per cell,
+//    see tail.cu), so a 1d point-step is 7 FP64 instructions; 2d/3d use the cubic B-spline window (16/64
+//    doubles) with value and derivative bases computed once per dimension and shared by the field components.
 #include "internal.cuh"
+
+#include <cstdio>
+#include <cstdlib>
 
 namespace nufi_b200
 {
@@ -29,25 +36,29 @@ namespace
 
 constexpr double kMagic = 6755399441055744.0; // 1.5 * 2^52: adding it rounds to the nearest integer
 
-__device__ __forceinline__ int wrap_cell(int k, int N)
+// Periodic cell index after a move of dk cells.  POW2: mask.  Otherwise one conditional correction each way;
+// anything further out (a point crossing more than a whole period in one step) is clamped into range and
+// flagged -- such points are recomputed by the robust slow path after the trace.
+template <bool POW2> __device__ __forceinline__ int wrap_cell(int k, int N, unsigned &bad)
 {
-    if (k < 0) k += N;
-    if (k >= N) k -= N;
-    if (static_cast<unsigned>(k) >= static_cast<unsigned>(N)) { // more than one period in a single step: rare
-        k %= N;
+    if constexpr (POW2) {
+        return k & (N - 1);
+    } else {
         if (k < 0) k += N;
+        if (k >= N) k -= N;
+        const unsigned kc = min(static_cast<unsigned>(k), static_cast<unsigned>(N - 1));
+        bad |= kc ^ static_cast<unsigned>(k);
+        return static_cast<int>(kc);
     }
-    return k;
 }
 
 // t2 = tau - drift.  New cell/offset such that k + 1/2 + tau is preserved and tau in [-1/2, 1/2].
-__device__ __forceinline__ void relocate(double &tau, int &k, double t2, int N)
+template <bool POW2> __device__ __forceinline__ void relocate(double &tau, int &k, double t2, int N, unsigned &bad)
 {
     const double y = t2 + kMagic;
-    const int dk = __double2loint(y);
     const double r = y - kMagic;
     tau = t2 - r;
-    k = wrap_cell(k + dk, N);
+    k = wrap_cell<POW2>(k + __double2loint(y), N, bad);
 }
 
 // Cubic B-spline basis on a cell, t = 1/2 + tau.  Returns 6*N_a(t) and 2*N'_a(t) (nufi/splines.hpp:39-79
@@ -118,51 +129,61 @@ template <int DIM> struct Point
     int cell[DIM];
 };
 
-// cd = cx*d (d = 0 for eval_f's initial half kick, which does not drift), hg = h*g (h = 1/2 for half kicks)
-template <bool STAGED>
-__device__ __forceinline__ void step1d(Point<1> &p, const double *lev, const BtParams &P, double d, double h)
+// Step kinds: FULL = drift + full kick (levels n-1..1, the inner loop); LAST = drift + half kick (level 0);
+// FIRST = half kick without drift (eval_f's initial half step on level n).
+enum StepKind { FULL = 0, LAST = 1, FIRST = 2 };
+
+template <int KIND, bool STAGED, bool POW2>
+__device__ __forceinline__ void step1d(Point<1> &p, const double *lev, const BtParams &P, unsigned &bad)
 {
-    relocate(p.tau[0], p.cell[0], fma(-P.cx * d, p.vel[0], p.tau[0]), P.Nx);
-    const double *c = lev + p.cell[0];
-    const double p0 = ld<STAGED>(c), p1 = ld<STAGED>(c + P.sx), p2 = ld<STAGED>(c + 2 * P.sx);
+    if constexpr (KIND != FIRST) relocate<POW2>(p.tau[0], p.cell[0], fma(P.ncx, p.vel[0], p.tau[0]), P.Nx, bad);
+    const double *c = lev + 3 * p.cell[0];
+    const double p0 = ld<STAGED>(c), p1 = ld<STAGED>(c + 1), p2 = ld<STAGED>(c + 2);
     const double t = p.tau[0];
-    p.vel[0] = fma(h, fma(t, fma(t, p2, p1), p0), p.vel[0]);
+    const double q = fma(t, p2, p1);
+    if constexpr (KIND == FULL) p.vel[0] = fma(t, q, p0 + p.vel[0]);
+    else p.vel[0] = fma(0.5, fma(t, q, p0), p.vel[0]);
 }
 
-template <bool STAGED>
-__device__ __forceinline__ void step2d(Point<2> &p, const double *lev, const BtParams &P, double d, double h)
+template <int KIND, bool STAGED, bool POW2>
+__device__ __forceinline__ void step2d(Point<2> &p, const double *lev, const BtParams &P, unsigned &bad)
 {
-    relocate(p.tau[0], p.cell[0], fma(-P.cx * d, p.vel[0], p.tau[0]), P.Nx);
-    relocate(p.tau[1], p.cell[1], fma(-P.cy * d, p.vel[1], p.tau[1]), P.Ny);
+    if constexpr (KIND != FIRST) {
+        relocate<POW2>(p.tau[0], p.cell[0], fma(P.ncx, p.vel[0], p.tau[0]), P.Nx, bad);
+        relocate<POW2>(p.tau[1], p.cell[1], fma(P.ncy, p.vel[1], p.tau[1]), P.Ny, bad);
+    }
     double Nx[4], Dx[4], Ny[4], Dy[4];
     basis4(p.tau[0], Nx, Dx);
     basis4(p.tau[1], Ny, Dy);
-    const double *row = lev + p.cell[1] * P.sx + p.cell[0];
+    const double *row = lev + (p.cell[1] * P.sx + p.cell[0]);
     double Sx = 0, Sy = 0;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
         const double c0 = ld<STAGED>(row), c1 = ld<STAGED>(row + 1), c2 = ld<STAGED>(row + 2), c3 = ld<STAGED>(row + 3);
         const double pv = fma(c3, Nx[3], fma(c2, Nx[2], fma(c1, Nx[1], c0 * Nx[0])));
         const double qv = fma(c3, Dx[3], fma(c2, Dx[2], fma(c1, Dx[1], c0 * Dx[0])));
-        Sx = fma(Ny[b], qv, Sx);
-        Sy = fma(Dy[b], pv, Sy);
+        if (b == 0) { Sx = Ny[0] * qv; Sy = Dy[0] * pv; }
+        else { Sx = fma(Ny[b], qv, Sx); Sy = fma(Dy[b], pv, Sy); }
         row += P.sx;
     }
+    const double h = KIND == FULL ? 1.0 : 0.5;
     p.vel[0] = fma(h * P.gx, Sx, p.vel[0]);
     p.vel[1] = fma(h * P.gy, Sy, p.vel[1]);
 }
 
-template <bool STAGED>
-__device__ __forceinline__ void step3d(Point<3> &p, const double *lev, const BtParams &P, double d, double h)
+template <int KIND, bool STAGED, bool POW2>
+__device__ __forceinline__ void step3d(Point<3> &p, const double *lev, const BtParams &P, unsigned &bad)
 {
-    relocate(p.tau[0], p.cell[0], fma(-P.cx * d, p.vel[0], p.tau[0]), P.Nx);
-    relocate(p.tau[1], p.cell[1], fma(-P.cy * d, p.vel[1], p.tau[1]), P.Ny);
-    relocate(p.tau[2], p.cell[2], fma(-P.cz * d, p.vel[2], p.tau[2]), P.Nz);
+    if constexpr (KIND != FIRST) {
+        relocate<POW2>(p.tau[0], p.cell[0], fma(P.ncx, p.vel[0], p.tau[0]), P.Nx, bad);
+        relocate<POW2>(p.tau[1], p.cell[1], fma(P.ncy, p.vel[1], p.tau[1]), P.Ny, bad);
+        relocate<POW2>(p.tau[2], p.cell[2], fma(P.ncz, p.vel[2], p.tau[2]), P.Nz, bad);
+    }
     double Nx[4], Dx[4], Ny[4], Dy[4], Nz[4], Dz[4];
     basis4(p.tau[0], Nx, Dx);
     basis4(p.tau[1], Ny, Dy);
     basis4(p.tau[2], Nz, Dz);
-    const double *plane = lev + p.cell[2] * P.sxy + p.cell[1] * P.sx + p.cell[0];
+    const double *plane = lev + (p.cell[2] * P.sxy + p.cell[1] * P.sx + p.cell[0]);
     double Sx = 0, Sy = 0, Sz = 0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -173,27 +194,54 @@ __device__ __forceinline__ void step3d(Point<3> &p, const double *lev, const BtP
             const double c0 = ld<STAGED>(row), c1 = ld<STAGED>(row + 1), c2 = ld<STAGED>(row + 2), c3 = ld<STAGED>(row + 3);
             const double pv = fma(c3, Nx[3], fma(c2, Nx[2], fma(c1, Nx[1], c0 * Nx[0])));
             const double qv = fma(c3, Dx[3], fma(c2, Dx[2], fma(c1, Dx[1], c0 * Dx[0])));
-            r = fma(Ny[b], qv, r);
-            s = fma(Dy[b], pv, s);
-            w = fma(Ny[b], pv, w);
+            if (b == 0) { r = Ny[0] * qv; s = Dy[0] * pv; w = Ny[0] * pv; }
+            else { r = fma(Ny[b], qv, r); s = fma(Dy[b], pv, s); w = fma(Ny[b], pv, w); }
             row += P.sx;
         }
-        Sx = fma(Nz[c], r, Sx);
-        Sy = fma(Nz[c], s, Sy);
-        Sz = fma(Dz[c], w, Sz);
+        if (c == 0) { Sx = Nz[0] * r; Sy = Nz[0] * s; Sz = Dz[0] * w; }
+        else { Sx = fma(Nz[c], r, Sx); Sy = fma(Nz[c], s, Sy); Sz = fma(Dz[c], w, Sz); }
         plane += P.sxy;
     }
+    const double h = KIND == FULL ? 1.0 : 0.5;
     p.vel[0] = fma(h * P.gx, Sx, p.vel[0]);
     p.vel[1] = fma(h * P.gy, Sy, p.vel[1]);
     p.vel[2] = fma(h * P.gz, Sz, p.vel[2]);
 }
 
-template <int DIM, bool STAGED>
-__device__ __forceinline__ void step(Point<DIM> &p, const double *lev, const BtParams &P, double d, double h)
+template <int DIM, int KIND, bool STAGED, bool POW2>
+__device__ __forceinline__ void step(Point<DIM> &p, const double *lev, const BtParams &P, unsigned &bad)
 {
-    if constexpr (DIM == 1) step1d<STAGED>(p, lev, P, d, h);
-    else if constexpr (DIM == 2) step2d<STAGED>(p, lev, P, d, h);
-    else step3d<STAGED>(p, lev, P, d, h);
+    if constexpr (DIM == 1) step1d<KIND, STAGED, POW2>(p, lev, P, bad);
+    else if constexpr (DIM == 2) step2d<KIND, STAGED, POW2>(p, lev, P, bad);
+    else step3d<KIND, STAGED, POW2>(p, lev, P, bad);
+}
+
+// Robust (slow) trace of one point straight from the global history: used only for points whose fast trace
+// flagged a multi-period jump (wrap_cell).  Same arithmetic, cell index reduced with a true modulo; a full
+// kick is applied as two half kicks from the same position.
+template <int DIM> __device__ __noinline__ void slow_trace(Point<DIM> &p, const BtParams &P)
+{
+    const int Ns[3] = {P.Nx, P.Ny, P.Nz};
+    const double nc[3] = {P.ncx, P.ncy, P.ncz};
+    for (int m = P.first_level; m >= 0; --m) {
+        const double *lev = P.hist + static_cast<size_t>(m) * (P.level_bytes / 8);
+        const bool first = P.metrics && m == P.first_level;
+        if (!first) {
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                const double t2 = fma(nc[d], p.vel[d], p.tau[d]);
+                const double r = rint(t2);
+                p.tau[d] = t2 - r;
+                long long k = static_cast<long long>(p.cell[d]) + static_cast<long long>(r);
+                k %= Ns[d];
+                if (k < 0) k += Ns[d];
+                p.cell[d] = static_cast<int>(k);
+            }
+        }
+        unsigned bad = 0;
+        step<DIM, FIRST, false, false>(p, lev, P, bad);
+        if (!(first || m == 0)) step<DIM, FIRST, false, false>(p, lev, P, bad);
+    }
 }
 
 // ---------------------------------------------------------------- mbarrier / bulk-copy primitives (PTX)
@@ -233,34 +281,39 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// named barrier over the consumer warps only (the producer warp never joins)
+__device__ __forceinline__ void consumer_sync(unsigned threads) { asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); }
 
-constexpr int kMaxStages = 16;
-constexpr unsigned kBarBytes = 2 * kMaxStages * 8; // full[16], empty[16]
+constexpr int kMaxStages = 8;
+constexpr unsigned kBarBytes = 2 * kMaxStages * 8; // full[8], empty[8]
+constexpr unsigned kRedBytes = 32 * 32 * 8;        // consumer-warp reduction scratch [32 warps][32 lanes]
+constexpr unsigned kSmemFixed = kBarBytes + kRedBytes;
 
 template <int DIM, int ILP> struct Tune
 {
-    // consumer warps per CTA upper bound (register budget), chosen from -Xptxas -v
+    // thread-count upper bound handed to __launch_bounds__ (sets the register budget)
     static constexpr int max_threads = DIM == 1 ? 1024 : (DIM == 2 ? (ILP == 1 ? 768 : 512) : (ILP == 1 ? 512 : 256));
 };
 
 // ---------------------------------------------------------------- the kernel
-template <int DIM, int ILP, bool STAGED>
+template <int DIM, int ILP, bool STAGED, bool POW2>
 __global__ void __launch_bounds__(Tune<DIM, ILP>::max_threads, 1) backtrace_kernel(const __grid_constant__ BtParams P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ double red[32][4];
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);
+    unsigned long long *empty = full + kMaxStages;
+    double(*sred)[32] = reinterpret_cast<double(*)[32]>(smem + kBarBytes);
+    const unsigned char *ring = smem + kSmemFixed;
 
     const int lane = threadIdx.x & 31;
     const unsigned warp = threadIdx.x >> 5;
     const unsigned W = P.W;
-    const unsigned long long cta_first = static_cast<unsigned long long>(blockIdx.x) * W * P.rounds;
-    if (cta_first >= P.n_units) return; // whole CTA idle (uniform)
-    unsigned long long left = P.n_units - cta_first;
-    const unsigned rounds = static_cast<unsigned>(min(static_cast<unsigned long long>(P.rounds), (left + W - 1) / W));
-
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);
-    unsigned long long *empty = full + kMaxStages;
-    double *ring = reinterpret_cast<double *>(smem + kBarBytes);
+    // this CTA's run of CTA-rounds
+    const unsigned g0 = blockIdx.x * P.rpc;
+    if (g0 >= P.R) return; // whole CTA idle (uniform)
+    const unsigned my_rounds = min(P.rpc, P.R - g0);
+    const unsigned t_first = g0 / P.rpt;
+    const int c_hi = P.first_level >= 0 ? P.first_level / P.Lc : -1;
     const unsigned level_doubles = P.level_bytes / 8;
 
     if constexpr (STAGED) {
@@ -274,136 +327,188 @@ __global__ void __launch_bounds__(Tune<DIM, ILP>::max_threads, 1) backtrace_kern
         __syncthreads();
     }
 
-    double m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-
     if (STAGED && warp == W) {
-        // ------------------------------------------------ producer warp: stream levels newest -> oldest, once per round
+        // ------------------------------------------------ producer warp: stream chunks newest -> oldest, once per round
         if (lane == 0) {
             int s = 0;
             unsigned ph = 0;
             bool primed = false;
-            for (unsigned r = 0; r < rounds; ++r)
-                for (int m = P.first_level; m >= 0; --m) {
+            for (unsigned r = 0; r < my_rounds; ++r)
+                for (int c = c_hi; c >= 0; --c) {
                     if (primed) mbar_wait(&empty[s], ph ^ 1u);
-                    mbar_expect_tx(&full[s], P.level_bytes);
-                    const unsigned char *src = reinterpret_cast<const unsigned char *>(P.hist + static_cast<unsigned long long>(m) * P.level_stride);
-                    unsigned char *dst = reinterpret_cast<unsigned char *>(ring + static_cast<size_t>(s) * level_doubles);
-                    for (unsigned off = 0; off < P.level_bytes; off += 32768u)
-                        bulk_g2s(dst + off, src + off, min(32768u, P.level_bytes - off), &full[s]);
+                    const int lv_top = c == c_hi ? P.first_level - c * P.Lc : P.Lc - 1;
+                    const unsigned bytes = static_cast<unsigned>(lv_top + 1) * P.level_bytes;
+                    mbar_expect_tx(&full[s], bytes);
+                    const unsigned char *src =
+                        reinterpret_cast<const unsigned char *>(P.hist) + static_cast<size_t>(c) * P.Lc * P.level_bytes;
+                    unsigned char *dst = const_cast<unsigned char *>(ring) + static_cast<size_t>(s) * P.stage_bytes;
+                    for (unsigned off = 0; off < bytes; off += 32768u)
+                        bulk_g2s(dst + off, src + off, min(32768u, bytes - off), &full[s]);
                     if (++s == P.stages) { s = 0; ph ^= 1u; primed = true; }
                 }
         }
-    } else {
-        // ------------------------------------------------ consumer warps
-        double acc = 0;
-        long long cur_tile = -1;
-        int s = 0;
-        unsigned ph = 0;
-        for (unsigned r = 0; r < rounds; ++r) {
-            const unsigned long long unit = cta_first + static_cast<unsigned long long>(r) * W + warp;
-            const bool unit_ok = unit < P.n_units;
-            const unsigned long long tile = unit_ok ? unit / P.units_per_tile : 0ull;
-            const unsigned long long jc = unit_ok ? unit % P.units_per_tile : 0ull;
-            if (unit_ok && static_cast<long long>(tile) != cur_tile) {
-                if (cur_tile >= 0 && !P.metrics) P.partials[((blockIdx.x + cur_tile) * W + warp) * 32 + lane] = acc;
-                acc = 0;
-                cur_tile = static_cast<long long>(tile);
-            }
-            unsigned long long l = P.l_first + tile * 32 + lane;
-            const bool node_ok = unit_ok && l <= P.l_last;
-            if (!node_ok) l = P.l_first;
-            int ix, iy = 0, iz = 0;
-            {
-                unsigned long long t = l;
-                ix = static_cast<int>(t % P.Nx);
-                t /= P.Nx;
-                if (DIM >= 2) { iy = static_cast<int>(t % P.Ny); t /= P.Ny; }
-                if (DIM >= 3) iz = static_cast<int>(t);
-            }
+        return;
+    }
 
-            Point<DIM> pt[ILP];
-            bool ok[ILP];
-            double v0[ILP][DIM]; // starting velocities (metrics need them)
-#pragma unroll
-            for (int i = 0; i < ILP; ++i) {
-                unsigned long long j = jc * ILP + i;
-                ok[i] = node_ok && j < P.Nvel;
-                const unsigned long long q = l * P.Nvel + j;
-                ok[i] = ok[i] && q >= P.q_begin && q < P.q_end;
-                if (j >= P.Nvel) j = 0;
-                const int iu = static_cast<int>(j % P.Nu);
-                const int iv = DIM >= 2 ? static_cast<int>((j / P.Nu) % P.Nv) : 0;
-                const int iw = DIM >= 3 ? static_cast<int>(j / (static_cast<unsigned long long>(P.Nu) * P.Nv)) : 0;
-                // node ix sits on the left edge of cell ix: xi = ix  ->  tau = -1/2
-                pt[i].cell[0] = ix;
-                pt[i].tau[0] = -0.5;
-                pt[i].vel[0] = P.metrics ? P.ug0 + iu * P.dug : P.u0 + iu * P.du;
-                if constexpr (DIM >= 2) {
-                    pt[i].cell[1] = iy;
-                    pt[i].tau[1] = -0.5;
-                    pt[i].vel[1] = P.metrics ? P.vg0 + iv * P.dvg : P.v0 + iv * P.dv;
-                }
-                if constexpr (DIM >= 3) {
-                    pt[i].cell[2] = iz;
-                    pt[i].tau[2] = -0.5;
-                    pt[i].vel[2] = P.metrics ? P.wg0 + iw * P.dwg : P.w0 + iw * P.dw;
-                }
-#pragma unroll
-                for (int dd = 0; dd < DIM; ++dd) v0[i][dd] = pt[i].vel[dd];
-            }
+    // ---------------------------------------------------- consumer warps
+    double acc = 0;
+    double m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    unsigned cur_tile = t_first;
+    int s = 0;
+    unsigned ph = 0;
 
-            for (int m = P.first_level; m >= 0; --m) {
-                const double *lev;
-                if constexpr (STAGED) {
+    auto flush_tile = [&](unsigned tile) { // CTA-uniform: every consumer warp calls it
+        sred[warp][lane] = acc;
+        consumer_sync(W * 32);
+        if (warp == 0) {
+            double sum = 0;
+            for (unsigned w = 0; w < W; ++w) sum += sred[w][lane];
+            P.slots[(static_cast<size_t>(blockIdx.x) * P.Tmax + (tile - t_first)) * 32 + lane] = sum;
+        }
+        consumer_sync(W * 32);
+        acc = 0;
+    };
+
+    for (unsigned r = 0; r < my_rounds; ++r) {
+        const unsigned g = g0 + r;
+        const unsigned tile = g / P.rpt;
+        const unsigned jr = g - tile * P.rpt;
+        if (tile != cur_tile) {
+            if (!P.metrics) flush_tile(cur_tile);
+            cur_tile = tile;
+        }
+        const unsigned jc = jr * W + warp;
+        if (jc >= P.upt) { // no unit for this warp in this round: keep the stage protocol going
+            if constexpr (STAGED) {
+                for (int c = c_hi; c >= 0; --c) {
                     mbar_wait(&full[s], ph);
-                    lev = ring + static_cast<size_t>(s) * level_doubles;
-                } else {
-                    lev = P.hist + static_cast<unsigned long long>(m) * P.level_stride;
-                }
-                const bool first = P.metrics && m == P.first_level; // eval_f: half kick at the start, no drift
-                const double h = (m == 0 || first) ? 0.5 : 1.0;
-                const double d = first ? 0.0 : 1.0;
-#pragma unroll
-                for (int i = 0; i < ILP; ++i) step<DIM, STAGED>(pt[i], lev, P, d, h);
-                if constexpr (STAGED) {
-                    __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[s]);
                     if (++s == P.stages) { s = 0; ph ^= 1u; }
                 }
             }
+            continue;
+        }
+
+        unsigned long long l = P.l_first + static_cast<unsigned long long>(tile) * 32 + lane;
+        const bool node_ok = l <= P.l_last;
+        if (!node_ok) l = P.l_first;
+        int ix, iy = 0, iz = 0;
+        {
+            unsigned long long t = l;
+            ix = static_cast<int>(t % P.Nx);
+            t /= P.Nx;
+            if (DIM >= 2) { iy = static_cast<int>(t % P.Ny); t /= P.Ny; }
+            if (DIM >= 3) iz = static_cast<int>(t);
+        }
+
+        Point<DIM> pt[ILP];
+        bool ok[ILP];
+        unsigned bad[ILP];
+        double v0[ILP][DIM]; // starting velocities (metrics need them; the slow path restarts from them)
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            unsigned long long j = static_cast<unsigned long long>(jc) * ILP + i;
+            ok[i] = node_ok && j < P.Nvel;
+            const unsigned long long q = l * P.Nvel + j;
+            ok[i] = ok[i] && q >= P.q_begin && q < P.q_end;
+            if (j >= P.Nvel) j = 0;
+            const int iu = static_cast<int>(j % P.Nu);
+            const int iv = DIM >= 2 ? static_cast<int>((j / P.Nu) % P.Nv) : 0;
+            const int iw = DIM >= 3 ? static_cast<int>(j / (static_cast<unsigned long long>(P.Nu) * P.Nv)) : 0;
+            bad[i] = 0;
+            // node ix sits on the left edge of cell ix: xi = ix  ->  tau = -1/2
+            pt[i].cell[0] = ix;
+            pt[i].tau[0] = -0.5;
+            pt[i].vel[0] = P.metrics ? P.ug0 + iu * P.dug : P.u0 + iu * P.du;
+            if constexpr (DIM >= 2) {
+                pt[i].cell[1] = iy;
+                pt[i].tau[1] = -0.5;
+                pt[i].vel[1] = P.metrics ? P.vg0 + iv * P.dvg : P.v0 + iv * P.dv;
+            }
+            if constexpr (DIM >= 3) {
+                pt[i].cell[2] = iz;
+                pt[i].tau[2] = -0.5;
+                pt[i].vel[2] = P.metrics ? P.wg0 + iw * P.dwg : P.w0 + iw * P.dw;
+            }
+#pragma unroll
+            for (int dd = 0; dd < DIM; ++dd) v0[i][dd] = pt[i].vel[dd];
+        }
+
+        // ---- the trace: chunks newest -> oldest; inside a chunk levels top -> bottom
+        for (int c = c_hi; c >= 0; --c) {
+            const double *base;
+            int j = c == c_hi ? P.first_level - c * P.Lc : P.Lc - 1;
+            if constexpr (STAGED) {
+                mbar_wait(&full[s], ph);
+                base = reinterpret_cast<const double *>(ring + static_cast<size_t>(s) * P.stage_bytes);
+            } else {
+                base = P.hist + static_cast<size_t>(c) * P.Lc * level_doubles;
+            }
+            const double *lev = base + static_cast<size_t>(j) * level_doubles;
+            if (P.metrics && c == c_hi) { // eval_f: half kick on level n at the starting position
+#pragma unroll
+                for (int i = 0; i < ILP; ++i) step<DIM, FIRST, STAGED, POW2>(pt[i], lev, P, bad[i]);
+                --j;
+                lev -= level_doubles;
+            }
+            const int j_lo = c == 0 ? 1 : 0;
+#pragma unroll 2
+            for (; j >= j_lo; --j) {
+#pragma unroll
+                for (int i = 0; i < ILP; ++i) step<DIM, FULL, STAGED, POW2>(pt[i], lev, P, bad[i]);
+                lev -= level_doubles;
+            }
+            if (c == 0 && j == 0) { // level 0: drift + half kick
+#pragma unroll
+                for (int i = 0; i < ILP; ++i) step<DIM, LAST, STAGED, POW2>(pt[i], base, P, bad[i]);
+            }
+            if constexpr (STAGED) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                if (++s == P.stages) { s = 0; ph ^= 1u; }
+            }
+        }
 
 #pragma unroll
-            for (int i = 0; i < ILP; ++i) {
-                // foot of the characteristic in physical coordinates (periodic image inside the box)
-                const double x = P.x_min + (pt[i].cell[0] + (0.5 + pt[i].tau[0])) * P.dx;
-                double f;
-                if constexpr (DIM == 1) f = f0_1d(P, x, pt[i].vel[0]);
-                else if constexpr (DIM == 2) {
-                    const double y = P.y_min + (pt[i].cell[1] + (0.5 + pt[i].tau[1])) * P.dy;
-                    f = f0_2d(P, x, y, pt[i].vel[0], pt[i].vel[1]);
-                } else {
-                    const double y = P.y_min + (pt[i].cell[1] + (0.5 + pt[i].tau[1])) * P.dy;
-                    const double z = P.z_min + (pt[i].cell[2] + (0.5 + pt[i].tau[2])) * P.dz;
-                    f = f0_3d(P, x, y, z, pt[i].vel[0], pt[i].vel[1], pt[i].vel[2]);
-                }
-                if (ok[i]) {
-                    acc += f;
-                    if (P.metrics) { // nufi/cuda_kernel.cu:72-78, 264-270, 459-465
-                        double vsq = v0[i][0] * v0[i][0];
-                        if constexpr (DIM >= 2) vsq += v0[i][1] * v0[i][1];
-                        if constexpr (DIM >= 3) vsq += v0[i][2] * v0[i][2];
-                        m0 += P.mweight * f;
-                        m1 += P.mweight * f * f;
-                        m2 += DIM == 1 ? P.mweight * (vsq * f / 2) : P.mweight * vsq * f / 2;
-                        m3 += (f > 0) ? -P.mweight * f * log(f) : 0;
-                    }
+        for (int i = 0; i < ILP; ++i) {
+            if (!POW2 && bad[i]) { // a multi-period jump was clamped: redo this point on the robust path
+#pragma unroll
+                for (int dd = 0; dd < DIM; ++dd) { pt[i].vel[dd] = v0[i][dd]; pt[i].tau[dd] = -0.5; }
+                pt[i].cell[0] = ix;
+                if constexpr (DIM >= 2) pt[i].cell[1] = iy;
+                if constexpr (DIM >= 3) pt[i].cell[2] = iz;
+                slow_trace<DIM>(pt[i], P);
+            }
+            // foot of the characteristic in physical coordinates (periodic image inside the box)
+            const double x = P.x_min + (pt[i].cell[0] + (0.5 + pt[i].tau[0])) * P.dx;
+            double f;
+            if constexpr (DIM == 1) f = f0_1d(P, x, pt[i].vel[0]);
+            else if constexpr (DIM == 2) {
+                const double y = P.y_min + (pt[i].cell[1] + (0.5 + pt[i].tau[1])) * P.dy;
+                f = f0_2d(P, x, y, pt[i].vel[0], pt[i].vel[1]);
+            } else {
+                const double y = P.y_min + (pt[i].cell[1] + (0.5 + pt[i].tau[1])) * P.dy;
+                const double z = P.z_min + (pt[i].cell[2] + (0.5 + pt[i].tau[2])) * P.dz;
+                f = f0_3d(P, x, y, z, pt[i].vel[0], pt[i].vel[1], pt[i].vel[2]);
+            }
+            if (ok[i]) {
+                acc += f;
+                if (P.metrics) { // nufi/cuda_kernel.cu:72-78, 264-270, 459-465
+                    double vsq = v0[i][0] * v0[i][0];
+                    if constexpr (DIM >= 2) vsq += v0[i][1] * v0[i][1];
+                    if constexpr (DIM >= 3) vsq += v0[i][2] * v0[i][2];
+                    m0 += P.mweight * f;
+                    m1 += P.mweight * f * f;
+                    m2 += DIM == 1 ? P.mweight * (vsq * f / 2) : P.mweight * vsq * f / 2;
+                    m3 += (f > 0) ? -P.mweight * f * log(f) : 0;
                 }
             }
         }
-        if (cur_tile >= 0 && !P.metrics) P.partials[((blockIdx.x + cur_tile) * W + warp) * 32 + lane] = acc;
     }
 
-    if (P.metrics) { // deterministic block reduction of the four metric sums
+    if (!P.metrics) {
+        flush_tile(cur_tile);
+    } else { // deterministic block reduction of the four metric sums
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             m0 += __shfl_down_sync(0xffffffffu, m0, o);
@@ -411,37 +516,41 @@ __global__ void __launch_bounds__(Tune<DIM, ILP>::max_threads, 1) backtrace_kern
             m2 += __shfl_down_sync(0xffffffffu, m2, o);
             m3 += __shfl_down_sync(0xffffffffu, m3, o);
         }
-        if (lane == 0) { red[warp][0] = m0; red[warp][1] = m1; red[warp][2] = m2; red[warp][3] = m3; }
-        __syncthreads();
+        if (lane == 0) { sred[warp][0] = m0; sred[warp][1] = m1; sred[warp][2] = m2; sred[warp][3] = m3; }
+        consumer_sync(W * 32);
         if (threadIdx.x < 4) {
             double sum = 0;
-            for (unsigned w = 0; w < W; ++w) sum += red[w][threadIdx.x];
+            for (unsigned w = 0; w < W; ++w) sum += sred[w][threadIdx.x];
             P.mpartials[blockIdx.x * 4 + threadIdx.x] = sum;
         }
     }
 }
 
-// Adds the per-(CTA,warp,tile) slots in a fixed order.  One warp per tile of 32 nodes.
-__global__ void finish_rho_kernel(const __grid_constant__ FinishParams F)
+// Adds the per-(CTA, tile) slots of each tile in a fixed order.  One block (8 warps) per tile of 32 nodes.
+__global__ void __launch_bounds__(256) finish_rho_kernel(const __grid_constant__ FinishParams F)
 {
-    const unsigned tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ double part[8][32];
+    const unsigned tile = blockIdx.x;
     const int lane = threadIdx.x & 31;
-    if (tile >= F.n_tiles) return;
-    const unsigned long long per_cta = static_cast<unsigned long long>(F.W) * F.rounds;
-    const unsigned long long u_lo = static_cast<unsigned long long>(tile) * F.units_per_tile;
-    const unsigned long long u_hi = u_lo + F.units_per_tile - 1;
-    const unsigned c_lo = static_cast<unsigned>(u_lo / per_cta);
-    unsigned c_hi = static_cast<unsigned>(u_hi / per_cta);
-    if (c_hi >= F.grid) c_hi = F.grid - 1;
+    const unsigned wj = threadIdx.x >> 5;
+    const unsigned b_lo = (tile * F.rpt) / F.rpc;
+    const unsigned b_hi = ((tile + 1) * F.rpt - 1) / F.rpc;
     double sum = 0;
-    for (unsigned c = c_lo; c <= c_hi; ++c) {
-        const double *slot = F.partials + (static_cast<unsigned long long>(c + tile) * F.W) * 32 + lane;
-        for (unsigned w = 0; w < F.W; ++w) sum += slot[static_cast<size_t>(w) * 32];
+    for (unsigned b = b_lo + wj; b <= b_hi; b += 8) {
+        const unsigned t_first = (b * F.rpc) / F.rpt;
+        sum += F.slots[(static_cast<size_t>(b) * F.Tmax + (tile - t_first)) * 32 + lane];
     }
-    const unsigned long long l = F.l_first + static_cast<unsigned long long>(tile) * 32 + lane;
-    if (l <= F.l_last) {
-        F.rho_partial[l] = -F.dV * sum;
-        if (F.rho_full) F.rho_full[l] = 1 - F.dV * sum;
+    part[wj][lane] = sum;
+    __syncthreads();
+    if (wj == 0) {
+        double tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += part[w][lane];
+        const unsigned long long l = F.l_first + static_cast<unsigned long long>(tile) * 32 + lane;
+        if (l <= F.l_last) {
+            F.rho_partial[l] = -F.dV * tot;
+            if (F.rho_full) F.rho_full[l] = 1 - F.dV * tot;
+        }
     }
 }
 
@@ -454,10 +563,10 @@ __global__ void finish_metrics_kernel(const double *mpartials, unsigned grid, do
     }
 }
 
-template <int DIM, int ILP, bool STAGED>
+template <int DIM, int ILP, bool STAGED, bool POW2>
 cudaError_t launch_variant(const BtParams &P, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
 {
-    auto kern = backtrace_kernel<DIM, ILP, STAGED>;
+    auto kern = backtrace_kernel<DIM, ILP, STAGED, POW2>;
     if (smem_bytes > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
         if (e != cudaSuccess) return e;
@@ -466,15 +575,23 @@ cudaError_t launch_variant(const BtParams &P, unsigned grid, unsigned threads, s
     return cudaGetLastError();
 }
 
-template <int DIM>
-cudaError_t launch_dim(const BtParams &P, int ilp, bool staged, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
+template <int DIM, int ILP>
+cudaError_t launch_ilp(const BtParams &P, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
 {
-    if (ilp == 2) {
-        return staged ? launch_variant<DIM, 2, true>(P, grid, threads, smem_bytes, st)
-                      : launch_variant<DIM, 2, false>(P, grid, threads, smem_bytes, st);
+    if (staged) {
+        return pow2 ? launch_variant<DIM, ILP, true, true>(P, grid, threads, smem_bytes, st)
+                    : launch_variant<DIM, ILP, true, false>(P, grid, threads, smem_bytes, st);
     }
-    return staged ? launch_variant<DIM, 1, true>(P, grid, threads, smem_bytes, st)
-                  : launch_variant<DIM, 1, false>(P, grid, threads, smem_bytes, st);
+    return pow2 ? launch_variant<DIM, ILP, false, true>(P, grid, threads, smem_bytes, st)
+                : launch_variant<DIM, ILP, false, false>(P, grid, threads, smem_bytes, st);
+}
+
+template <int DIM>
+cudaError_t launch_dim(const BtParams &P, int ilp, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes,
+                       cudaStream_t st)
+{
+    return ilp == 2 ? launch_ilp<DIM, 2>(P, staged, pow2, grid, threads, smem_bytes, st)
+                    : launch_ilp<DIM, 1>(P, staged, pow2, grid, threads, smem_bytes, st);
 }
 
 int max_threads_for(int dim, int ilp)
@@ -484,24 +601,34 @@ int max_threads_for(int dim, int ilp)
     return ilp == 1 ? Tune<3, 1>::max_threads : Tune<3, 2>::max_threads;
 }
 
+bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
+
+int env_int(const char *name, int dflt)
+{
+    const char *v = std::getenv(name);
+    return v && *v ? std::atoi(v) : dflt;
+}
+
+// chains (warps x points per thread) per SM beyond which a CTA-round's time grows with its width
+int saturation_chains(int dim) { return dim == 1 ? 32 : (dim == 2 ? 24 : 16); }
+
 } // namespace
 
 // Host side: decomposition + launch.  q is the reference's flat quadrature index (cuda_kernel.cu:40-41,
 // 219-225, 402-412); [q_begin,q_end) may cut through a node's velocity range (masked per point).
-int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool metrics)
+int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool metrics, bool defer_finish)
 {
     const nufi_b200_config3d &c = h->c;
     BtParams P{};
     P.dim = h->dim;
     P.Nx = static_cast<int>(c.Nx); P.Ny = static_cast<int>(c.Ny); P.Nz = static_cast<int>(c.Nz);
     P.Nu = static_cast<int>(c.Nu); P.Nv = static_cast<int>(c.Nv); P.Nw = static_cast<int>(c.Nw);
-    P.sx = h->dim == 1 ? h->Nxp : h->sx;
+    P.sx = h->sx;
     P.sxy = h->sxy;
-    P.level_stride = h->level_stride;
     P.hist = h->d_hist;
     P.first_level = metrics ? (n == 0 ? -1 : static_cast<int>(n)) : static_cast<int>(n) - 1;
     P.metrics = metrics ? 1 : 0;
-    P.cx = c.dt * c.dx_inv; P.cy = c.dt * c.dy_inv; P.cz = c.dt * c.dz_inv;
+    P.ncx = -(c.dt * c.dx_inv); P.ncy = -(c.dt * c.dy_inv); P.ncz = -(c.dt * c.dz_inv);
     const double scale = h->dim == 2 ? 12.0 : 72.0;
     P.gx = -c.dt * c.dx_inv / scale; P.gy = -c.dt * c.dy_inv / scale; P.gz = -c.dt * c.dz_inv / scale;
     P.x_min = c.x_min; P.y_min = c.y_min; P.z_min = c.z_min;
@@ -527,43 +654,73 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     P.n_tiles = static_cast<unsigned>((n_nodes_range + 31) / 32);
     P.level_bytes = static_cast<unsigned>(h->level_stride * 8);
 
-    // ---- variant and shape
-    const size_t ring_budget = h->smem_optin > kBarBytes + 1024 ? h->smem_optin - kBarBytes - 1024 : 0;
+    // ---- variant: stage the history through shared memory when at least two levels fit
+    const size_t ring_budget = h->smem_optin > kSmemFixed + 1024 ? h->smem_optin - kSmemFixed - 1024 : 0;
     bool staged = P.first_level >= 0 && 2ull * P.level_bytes <= ring_budget;
     if (h->variant_force == 1) staged = false;
     if (h->variant_force == 2 && 2ull * P.level_bytes > ring_budget)
         return fail(h, NUFI_B200_ERR_ARG, "staged variant forced but two levels do not fit in shared memory");
+    const bool pow2 = is_pow2(c.Nx) && is_pow2(c.Ny) && is_pow2(c.Nz);
     const unsigned grid = static_cast<unsigned>(h->sm_count);
-    const unsigned long long warp_tasks = static_cast<unsigned long long>(P.n_tiles) * P.Nvel;
-    // two points per thread once there is more than one resident warp-task per consumer warp
-    int ilp = 1;
-    {
-        const unsigned wmax1 = max_threads_for(h->dim, 1) / 32 - (staged ? 1 : 0);
-        if (warp_tasks > static_cast<unsigned long long>(grid) * wmax1) ilp = 2;
-    }
-    const unsigned wmax = max_threads_for(h->dim, ilp) / 32 - (staged ? 1 : 0);
-    P.units_per_tile = (P.Nvel + ilp - 1) / ilp;
-    P.n_units = P.units_per_tile * P.n_tiles;
-    unsigned long long w_need = (P.n_units + grid - 1) / grid;
-    P.W = static_cast<unsigned>(w_need < wmax ? (w_need < 1 ? 1 : w_need) : wmax);
-    P.rounds = static_cast<unsigned>((P.n_units + static_cast<unsigned long long>(grid) * P.W - 1) / (static_cast<unsigned long long>(grid) * P.W));
-    if (P.rounds == 0) P.rounds = 1;
-    // rebalance: spread the same number of rounds over as few warps as needed
-    P.W = static_cast<unsigned>((P.n_units + static_cast<unsigned long long>(grid) * P.rounds - 1) / (static_cast<unsigned long long>(grid) * P.rounds));
-    if (P.W < 1) P.W = 1;
-    const unsigned threads = (P.W + (staged ? 1 : 0)) * 32;
-    size_t smem_bytes = 0;
+
+    // ---- chunking of the staged history
+    P.Lc = 1; P.stages = 0; P.stage_bytes = P.level_bytes;
     if (staged) {
-        int stages = static_cast<int>(ring_budget / P.level_bytes);
+        int Lc = static_cast<int>((32u * 1024u) / P.level_bytes);
+        Lc = env_int("NUFI_B200_LC", Lc);
+        Lc = Lc < 1 ? 1 : (Lc > 16 ? 16 : Lc);
+        while (Lc > 1 && 2ull * Lc * P.level_bytes > ring_budget) --Lc;
+        int stages = static_cast<int>(ring_budget / (static_cast<size_t>(Lc) * P.level_bytes));
         if (stages > kMaxStages) stages = kMaxStages;
-        if (stages > P.first_level + 1) stages = P.first_level + 1 > 2 ? P.first_level + 1 : 2;
-        P.stages = stages;
-        smem_bytes = kBarBytes + static_cast<size_t>(stages) * P.level_bytes;
+        const int n_chunks = P.first_level / Lc + 1;
+        if (stages > n_chunks) stages = n_chunks > 2 ? n_chunks : 2;
+        P.Lc = Lc; P.stages = stages; P.stage_bytes = static_cast<unsigned>(Lc) * P.level_bytes;
     }
 
-    // ---- partial slots
+    // ---- shape: points per thread (ILP) and consumer warps per CTA (W); a CTA-round = W warp-units of one tile
+    int best_ilp = 1;
+    unsigned best_W = 1;
+    {
+        double best_cost = 1e300;
+        const int csat = saturation_chains(h->dim);
+        const int force_ilp = env_int("NUFI_B200_ILP", 0), force_w = env_int("NUFI_B200_W", 0);
+        for (int ilp = 1; ilp <= 2; ++ilp) {
+            if (force_ilp && ilp != force_ilp) continue;
+            // 3d: one point per thread at 128 registers (16 warps) beats two points at 255 (8 warps) -- measured
+            if (!force_ilp && h->dim == 3 && ilp == 2) continue;
+            const unsigned wmax = max_threads_for(h->dim, ilp) / 32 - (staged ? 1 : 0);
+            const unsigned long long upt = (P.Nvel + ilp - 1) / ilp;
+            for (unsigned W = 1; W <= wmax; ++W) {
+                if (force_w && static_cast<int>(W) != force_w) continue;
+                const unsigned long long rpt = (upt + W - 1) / W;
+                const unsigned long long R = rpt * P.n_tiles;
+                const unsigned long long rpc = (R + grid - 1) / grid;
+                const unsigned long long ctas = (R + rpc - 1) / rpc;
+                const double chains = static_cast<double>(W) * ilp;
+                // time of a CTA-round ~ max(latency floor, throughput term); ILP 2 shares the per-level bookkeeping
+                double cost = static_cast<double>(rpc) * (chains > csat ? chains : csat) * (ilp == 2 ? 0.92 : 1.0);
+                cost *= 1.0 + 1e-3 * (static_cast<double>(grid) - static_cast<double>(ctas)) / grid; // prefer more busy SMs
+                cost *= 1.0 + 1e-4 * chains;                                                          // then narrower CTAs
+                if (cost < best_cost) { best_cost = cost; best_ilp = ilp; best_W = W; }
+            }
+        }
+        if (best_cost >= 1e300) return fail(h, NUFI_B200_ERR_ARG, "NUFI_B200_ILP / NUFI_B200_W override out of range");
+    }
+    const int ilp = best_ilp;
+    P.W = best_W;
+    P.upt = static_cast<unsigned>((P.Nvel + ilp - 1) / ilp);
+    P.rpt = (P.upt + P.W - 1) / P.W;
+    const unsigned long long R64 = static_cast<unsigned long long>(P.rpt) * P.n_tiles;
+    if (R64 >= (1ull << 31)) return fail(h, NUFI_B200_ERR_RANGE, "quadrature range too large for one launch");
+    P.R = static_cast<unsigned>(R64);
+    P.rpc = (P.R + grid - 1) / grid;
+    P.Tmax = (P.rpc - 1) / P.rpt + 2;
+    const unsigned threads = (P.W + (staged ? 1 : 0)) * 32;
+    const size_t smem_bytes = kSmemFixed + (staged ? static_cast<size_t>(P.stages) * P.stage_bytes : 0);
+
+    // ---- slots: one per (CTA, tile it touches); every slot the finish kernel reads is written by its CTA
     if (!metrics) {
-        const size_t need = (static_cast<size_t>(grid) + P.n_tiles) * P.W * 32;
+        const size_t need = static_cast<size_t>(grid) * P.Tmax * 32;
         if (need > h->partials_cap) {
             if (h->d_partials) cudaFree(h->d_partials);
             h->d_partials = nullptr;
@@ -572,8 +729,7 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
                 return fail(h, NUFI_B200_ERR_ALLOC, "cudaMalloc of the rho partial slots failed");
             h->partials_cap = need;
         }
-        NUFI_CUDA_CHECK(h, cudaMemsetAsync(h->d_partials, 0, need * sizeof(double), h->stream));
-        P.partials = h->d_partials;
+        P.slots = h->d_partials;
     } else {
         P.mpartials = h->d_mpartials;
         NUFI_CUDA_CHECK(h, cudaMemsetAsync(h->d_mpartials, 0, sizeof(double) * 4 * grid, h->stream));
@@ -586,33 +742,46 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     }
     NUFI_CUDA_CHECK(h, cudaEventRecord(ev_start, h->stream));
     cudaError_t e;
-    if (h->dim == 1) e = launch_dim<1>(P, ilp, staged, grid, threads, smem_bytes, h->stream);
-    else if (h->dim == 2) e = launch_dim<2>(P, ilp, staged, grid, threads, smem_bytes, h->stream);
-    else e = launch_dim<3>(P, ilp, staged, grid, threads, smem_bytes, h->stream);
+    if (h->dim == 1) e = launch_dim<1>(P, ilp, staged, pow2, grid, threads, smem_bytes, h->stream);
+    else if (h->dim == 2) e = launch_dim<2>(P, ilp, staged, pow2, grid, threads, smem_bytes, h->stream);
+    else e = launch_dim<3>(P, ilp, staged, pow2, grid, threads, smem_bytes, h->stream);
     NUFI_CUDA_CHECK(h, e);
     NUFI_CUDA_CHECK(h, cudaEventRecord(ev_stop, h->stream));
     h->ev_pending += 1;
     h->launches += 1;
-    h->last_variant = staged ? (ilp == 2 ? "smem-tma/ilp2" : "smem-tma/ilp1") : (ilp == 2 ? "global/ilp2" : "global/ilp1");
+    if (staged) std::snprintf(h->variant_buf, sizeof(h->variant_buf), "smem-tma/ilp%d/W%u/Lc%dx%d", ilp, P.W, P.Lc, P.stages);
+    else std::snprintf(h->variant_buf, sizeof(h->variant_buf), "global/ilp%d/W%u", ilp, P.W);
+    h->last_variant = h->variant_buf;
 
     if (!metrics) {
         FinishParams F{};
-        F.partials = h->d_partials;
+        F.slots = h->d_partials;
         F.rho_partial = h->d_rho_partial;
         const bool whole = q_begin == 0 && q_end == h->n_nodes * h->n_vel;
         F.rho_full = whole ? h->d_rho_full : nullptr;
         F.dV = h->dim == 1 ? P.du : (h->dim == 2 ? P.du * P.dv : P.du * P.dv * P.dw); // rho.hpp:145, 307, 459
-        F.l_first = P.l_first; F.l_last = P.l_last; F.n_nodes_total = h->n_nodes;
-        F.units_per_tile = P.units_per_tile;
-        F.n_tiles = P.n_tiles; F.rounds = P.rounds; F.W = P.W; F.grid = grid;
+        F.l_first = P.l_first; F.l_last = P.l_last;
+        F.rpt = P.rpt; F.rpc = P.rpc; F.Tmax = P.Tmax;
+        F.n_tiles = P.n_tiles;
         if (!whole) NUFI_CUDA_CHECK(h, cudaMemsetAsync(h->d_rho_partial, 0, sizeof(double) * h->n_nodes, h->stream));
-        const unsigned fb = 128, tiles_per_block = fb / 32;
-        finish_rho_kernel<<<(P.n_tiles + tiles_per_block - 1) / tiles_per_block, fb, 0, h->stream>>>(F);
-        NUFI_CUDA_CHECK(h, cudaGetLastError());
+        h->fin = F;
+        h->fin_pending = true;
+        if (!(defer_finish && whole)) return launch_finish(h);
+        return NUFI_B200_OK;
     } else {
         finish_metrics_kernel<<<1, 32, 0, h->stream>>>(h->d_mpartials, grid, h->d_metrics);
         NUFI_CUDA_CHECK(h, cudaGetLastError());
     }
+    h->launches += 1;
+    return NUFI_B200_OK;
+}
+
+int launch_finish(Handle *h)
+{
+    if (!h->fin_pending) return NUFI_B200_OK;
+    finish_rho_kernel<<<h->fin.n_tiles, 256, 0, h->stream>>>(h->fin);
+    NUFI_CUDA_CHECK(h, cudaGetLastError());
+    h->fin_pending = false;
     h->launches += 1;
     return NUFI_B200_OK;
 }

@@ -21,12 +21,12 @@ struct BtParams
 {
     int dim;
     int Nx, Ny, Nz, Nu, Nv, Nw;
-    int sx, sxy;                     // row / plane stride of a device level (doubles)
-    unsigned long long level_stride; // doubles between consecutive device levels
-    const double *hist;              // device history, device level format
+    int sx, sxy;                     // row / plane stride of a 2d/3d device level (doubles)
+    unsigned int level_bytes;        // bytes of one device level (multiple of 16)
+    const double *hist;              // device history, device level format, level m at m*level_bytes
     int first_level;                 // newest level read: n-1 (rho) or n (metrics); -1: none
-    int metrics;                     // 0: eval_ftilda -> rho partials; 1: eval_f -> metric partials
-    double cx, cy, cz;               // dt*dx_inv: cells per step per unit velocity
+    int metrics;                     // 0: eval_ftilda -> rho slots; 1: eval_f -> metric partials
+    double ncx, ncy, ncz;            // -dt*dx_inv: cells per step per unit velocity, negated (drift is backwards)
     double gx, gy, gz;               // kick factor -dt*dx_inv / (12 | 72) (2d | 3d basis scaling folded in)
     double x_min, y_min, z_min, dx, dy, dz;
     double u0, v0, w0, du, dv, dw;   // first midpoint velocity node and spacing, computed as rho.hpp does
@@ -37,24 +37,29 @@ struct BtParams
     unsigned long long q_begin, q_end, Nvel;
     unsigned long long l_first;      // first spatial node touched by [q_begin,q_end)
     unsigned long long l_last;       // last spatial node touched
-    unsigned long long units_per_tile, n_units;
-    unsigned int n_tiles, rounds, W;
-    double *partials;                // [(grid + n_tiles) * W][32]      (rho)
+    unsigned int n_tiles;            // tiles of 32 consecutive nodes
+    unsigned int upt;                // warp-units per tile = ceil(Nvel / ILP)
+    unsigned int W;                  // consumer warps per CTA
+    unsigned int rpt;                // CTA-rounds per tile = ceil(upt / W)
+    unsigned int R;                  // CTA-rounds in total = rpt * n_tiles
+    unsigned int rpc;                // CTA-rounds per CTA = ceil(R / grid)
+    unsigned int Tmax;               // slots per CTA (tiles one CTA can touch)
+    double *slots;                   // [grid][Tmax][32]                (rho)
     double *mpartials;               // [grid][4]                       (metrics)
     double mweight;
-    int stages;                      // shared-memory ring depth (staged variant)
-    unsigned int level_bytes;        // bytes of one device level (multiple of 16)
+    // staged variant: shared-memory ring of `stages` stages, each a chunk of Lc consecutive levels
+    int Lc, stages;
+    unsigned int stage_bytes;
 };
 
 struct FinishParams
 {
-    const double *partials;
+    const double *slots;
     double *rho_partial; // GPU convention: -dV * sum
     double *rho_full;    // CPU convention: 1 - dV * sum  (may be nullptr)
     double dV;
-    unsigned long long l_first, l_last, n_nodes_total;
-    unsigned long long units_per_tile;
-    unsigned int n_tiles, rounds, W, grid;
+    unsigned long long l_first, l_last;
+    unsigned int rpt, rpc, Tmax, n_tiles;
 };
 
 struct Handle
@@ -65,7 +70,7 @@ struct Handle
     size_t Nt = 0;
     size_t n_nodes = 0, n_vel = 0, stride_t = 0; // reference-format level size
     // device level format
-    int sx = 0, sxy = 0, Nxp = 0;
+    int sx = 0, sxy = 0;
     size_t level_stride = 0; // doubles
     size_t raw_stride = 0;   // 1d only: raw spline level kept beside the pp-form (doubles)
     double *d_hist = nullptr, *d_raw = nullptr;
@@ -83,6 +88,11 @@ struct Handle
     bool plans = false;
     cufftDoubleComplex *d_spec = nullptr;
     double *d_symbol = nullptr; // real part tables, see tail.cu
+    double *d_twiddle = nullptr; // per-dimension (cos, sin)(2 pi m / N_d) for the fused small-grid tail
+    int tail_force = 0;          // 0 auto, 1 cuFFT path, 2 fused single-CTA path
+    const char *last_tail = "none";
+    FinishParams fin{};          // slot reduction of the last backtrace launch
+    bool fin_pending = false;    // ... not yet run (the fused tail kernel does it itself)
     double *d_field = nullptr;
     double *d_epart = nullptr;
     size_t n_spec = 0;
@@ -97,6 +107,7 @@ struct Handle
     size_t smem_optin = 0;
     int variant_force = 0;
     const char *last_variant = "none";
+    char variant_buf[64] = {0};
     uint64_t launches = 0;
     std::string err;
 };
@@ -117,10 +128,13 @@ constexpr size_t kEvRingPairs = 256;
 int ev_acquire(Handle *h, cudaEvent_t *start, cudaEvent_t *stop); // next pair (drains the oldest when the ring is full)
 int ev_drain(Handle *h);                                          // blocking: fold all pending pairs into the totals
 // backtrace.cu
-int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool metrics);
+// defer_finish: leave the slot reduction to the field tail (fused step); otherwise finish_rho_kernel is launched
+int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool metrics, bool defer_finish = false);
+int launch_finish(Handle *h); // runs the pending slot reduction into d_rho_partial / d_rho_full
 // tail.cu
 int tail_init(Handle *h);
 void tail_destroy(Handle *h);
+// d_rho_full == nullptr: take rho from the pending slot reduction of the last backtrace launch
 int tail_run(Handle *h, size_t n, const double *d_rho_full);
 int convert_level_to_device(Handle *h, size_t n, const double *d_ref_level);  // reference format -> device format
 int convert_level_from_device(Handle *h, size_t n, double *d_ref_level);      // device format -> reference format

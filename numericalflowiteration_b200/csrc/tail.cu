@@ -21,7 +21,7 @@ namespace
 
 struct TailParams
 {
-    int Nx, Ny, Nz, Nxh;            // Nxh = Nx/2 + 1
+    int dim, Nx, Ny, Nz, Nxh;       // Nxh = Nx/2 + 1
     const double *kap2x, *kap2y, *kap2z; // per-dimension ii*ii*fac*fac
     const double2 *ilx, *ily, *ilz;      // per-dimension 1/lambda
     double fac_N;                   // 1/(Nx Ny Nz)
@@ -83,7 +83,7 @@ __device__ __forceinline__ void cell_poly_1d(const double *c, double g, double &
 
 struct ExpandParams
 {
-    int dim, Nx, Ny, Nz, sx, sxy, Nxp;
+    int dim, Nx, Ny, Nz, sx, sxy;
     size_t level_doubles; // device level size
     double g1;            // 1d: -dt*dx_inv
     int shift;            // 0: src indexed by periodic coefficient index
@@ -115,24 +115,24 @@ __global__ void expand_kernel(const double *src, double *level, ExpandParams E, 
     }
 }
 
-// 1d: raw level with halo + per-cell quadratics [p0 | p1 | p2], each Nxp long.
+// 1d: raw level with halo + per-cell quadratics, 3 consecutive doubles [p0 p1 p2] per cell (a stride of 3 doubles
+// keeps the 64-bit shared-memory loads of a warp's consecutive cells conflict-free).
 __global__ void expand1d_kernel(const double *src, double *raw, double *pp, ExpandParams E, const double *epart,
                                 unsigned n_epart, double vol_half, double *energy_out)
 {
     const int Nx = E.Nx;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Nx + 3; i += gridDim.x * blockDim.x) raw[i] = src[i % Nx];
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < E.Nxp; k += gridDim.x * blockDim.x) {
-        double p0 = 0, p1 = 0, p2 = 0;
-        if (k < Nx) {
-            double c[4];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < Nx; k += gridDim.x * blockDim.x) {
+        double p0, p1, p2;
+        double c[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) c[a] = src[(k + a) % Nx];
-            cell_poly_1d(c, E.g1, p0, p1, p2);
-        }
-        pp[k] = p0;
-        pp[E.Nxp + k] = p1;
-        pp[2 * E.Nxp + k] = p2;
+        for (int a = 0; a < 4; ++a) c[a] = src[(k + a) % Nx];
+        cell_poly_1d(c, E.g1, p0, p1, p2);
+        pp[3 * k] = p0;
+        pp[3 * k + 1] = p1;
+        pp[3 * k + 2] = p2;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (3 * Nx) % 2) pp[3 * Nx] = 0; // padding double
     if (energy_out && blockIdx.x == 0 && threadIdx.x == 0) {
         double s = 0;
         for (unsigned b = 0; b < n_epart; ++b) s += epart[b];
@@ -145,13 +145,14 @@ __global__ void ref_to_device_kernel(const double *ref, double *level, double *r
 {
     if (E.dim == 1) {
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < E.Nx + 3; i += gridDim.x * blockDim.x) raw1d[i] = ref[i];
-        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < E.Nxp; k += gridDim.x * blockDim.x) {
-            double p0 = 0, p1 = 0, p2 = 0;
-            if (k < E.Nx) cell_poly_1d(ref + k, E.g1, p0, p1, p2);
-            level[k] = p0;
-            level[E.Nxp + k] = p1;
-            level[2 * E.Nxp + k] = p2;
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < E.Nx; k += gridDim.x * blockDim.x) {
+            double p0, p1, p2;
+            cell_poly_1d(ref + k, E.g1, p0, p1, p2);
+            level[3 * k] = p0;
+            level[3 * k + 1] = p1;
+            level[3 * k + 2] = p2;
         }
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (3 * E.Nx) % 2) level[3 * E.Nx] = 0;
         return;
     }
     const size_t total = E.level_doubles;
@@ -192,12 +193,195 @@ __global__ void full_rho_kernel(const double *partial_sum, double *full, size_t 
         full[i] = 1 + partial_sum[i];
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused small-grid tail: ONE CTA does  [slot reduction ->] rho -> DFT -> Poisson x spline symbol -> inverse DFT ->
+// level n with halo (1d: raw level + per-cell quadratics) + energy.  For the grids the reference's drivers run
+// (256 / 32^2 / 8^3 ... 16^3 nodes) the four library launches of the cuFFT path cost more than the arithmetic; here
+// the transforms are direct separable sums over shared memory with exact twiddle tables (O(N * N_d), N <= 4096).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSmallMaxNodes = 4096;
+constexpr int kSmallMaxDim = 256;
+constexpr int kSmallThreads = 1024;
+
+struct SmallTailParams
+{
+    TailParams T;
+    ExpandParams E;
+    const double2 *twx, *twy, *twz; // (cos, sin)(2 pi m / N_d)
+    const double *rho;              // CPU-convention rho on the device, or nullptr: reduce the backtrace slots (F)
+    FinishParams F;
+    double *level, *raw1d, *energy_out;
+};
+
+// one separable pass along a dimension of length Nd (stride `stride`):  B[o] = sum_j A[base + j*stride] * w^(+-j*k)
+template <int SIGN>
+__device__ __forceinline__ void dft_pass(const double2 *A, double2 *B, int N, int Nd, int stride, const double2 *tw)
+{
+    for (int o = threadIdx.x; o < N; o += blockDim.x) {
+        const int k = (o / stride) % Nd;
+        const int base = o - k * stride;
+        double sr = 0, si = 0;
+        int idx = 0;
+        for (int j = 0; j < Nd; ++j) {
+            const double2 a = A[base + j * stride];
+            const double2 w = tw[idx];
+            if (SIGN < 0) { // a * (c - i s)
+                sr = fma(a.x, w.x, fma(a.y, w.y, sr));
+                si = fma(a.y, w.x, fma(-a.x, w.y, si));
+            } else { // a * (c + i s)
+                sr = fma(a.x, w.x, fma(-a.y, w.y, sr));
+                si = fma(a.y, w.x, fma(a.x, w.y, si));
+            }
+            idx += k;
+            if (idx >= Nd) idx -= Nd;
+        }
+        B[o] = make_double2(sr, si);
+    }
+}
+
+__global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __grid_constant__ SmallTailParams S)
+{
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    __shared__ double red[32];
+    const TailParams &T = S.T;
+    const int Nx = T.Nx, Ny = T.Ny, Nz = T.Nz;
+    const int N = Nx * Ny * Nz;
+    double2 *A = reinterpret_cast<double2 *>(sm_raw);
+    double2 *B = A + N;
+    double2 *twx = B + N, *twy = twx + Nx, *twz = twy + Ny;
+
+    // ---- rho (either given, or the fixed-order sum of the backtrace kernel's per-(CTA, tile) slots)
+    for (int l = threadIdx.x; l < N; l += blockDim.x) {
+        double r;
+        if (S.rho) {
+            r = S.rho[l];
+        } else {
+            const FinishParams &F = S.F;
+            const unsigned tile = static_cast<unsigned>(l) >> 5, lane = l & 31;
+            const unsigned b_lo = (tile * F.rpt) / F.rpc;
+            const unsigned b_hi = ((tile + 1) * F.rpt - 1) / F.rpc;
+            // same association as finish_rho_kernel: 8 strided partial sums, then added in order
+            double part[8];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) part[w] = 0;
+            for (unsigned b0 = b_lo; b0 <= b_hi; b0 += 8) {
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                    const unsigned b = b0 + w;
+                    if (b <= b_hi) {
+                        const unsigned t_first = (b * F.rpc) / F.rpt;
+                        part[w] += F.slots[(static_cast<size_t>(b) * F.Tmax + (tile - t_first)) * 32 + lane];
+                    }
+                }
+            }
+            double tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += part[w];
+            r = 1 - F.dV * tot;
+            F.rho_partial[l] = -F.dV * tot;
+            if (F.rho_full) F.rho_full[l] = r;
+        }
+        A[l] = make_double2(r, 0.0);
+    }
+    for (int i = threadIdx.x; i < Nx + Ny + Nz; i += blockDim.x) twx[i] = S.twx[i]; // the three tables are contiguous
+    __syncthreads();
+
+    // ---- forward transform, dimension by dimension
+    dft_pass<-1>(A, B, N, Nx, 1, twx);
+    __syncthreads();
+    double2 *cur = B, *oth = A;
+    if (T.dim >= 2) {
+        dft_pass<-1>(cur, oth, N, Ny, Nx, twy);
+        __syncthreads();
+        double2 *t = cur; cur = oth; oth = t;
+    }
+    if (T.dim >= 3) {
+        dft_pass<-1>(cur, oth, N, Nz, Nx * Ny, twz);
+        __syncthreads();
+        double2 *t = cur; cur = oth; oth = t;
+    }
+
+    // ---- Poisson x collocation symbol, energy in Fourier space (full spectrum: every mode counted once)
+    double e = 0;
+    for (int idx = threadIdx.x; idx < N; idx += blockDim.x) {
+        const int kx = idx % Nx;
+        const int rest = idx / Nx;
+        const int ky = rest % Ny;
+        const int kz = rest / Ny;
+        if (idx == 0) {
+            cur[0] = make_double2(0.0, 0.0);
+            continue;
+        }
+        const double2 Fk = cur[idx];
+        const double kap2 = T.kap2x[kx] + T.kap2y[ky] + T.kap2z[kz];
+        const double fac = T.fac_N / kap2;
+        const double pr = Fk.x * fac, pi = Fk.y * fac;
+        e += kap2 * (pr * pr + pi * pi);
+        const double2 a = T.ilx[kx], b = T.ily[ky], c = T.ilz[kz];
+        const double2 ab = make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+        const double2 s = make_double2(ab.x * c.x - ab.y * c.y, ab.x * c.y + ab.y * c.x);
+        cur[idx] = make_double2(pr * s.x - pi * s.y, pr * s.y + pi * s.x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0 && S.energy_out) {
+        double tot = 0;
+        for (unsigned w = 0; w < (blockDim.x >> 5); ++w) tot += red[w];
+        *S.energy_out = tot * T.vol_half;
+    }
+
+    // ---- inverse transform
+    dft_pass<1>(cur, oth, N, Nx, 1, twx);
+    __syncthreads();
+    { double2 *t = cur; cur = oth; oth = t; }
+    if (T.dim >= 2) {
+        dft_pass<1>(cur, oth, N, Ny, Nx, twy);
+        __syncthreads();
+        double2 *t = cur; cur = oth; oth = t;
+    }
+    if (T.dim >= 3) {
+        dft_pass<1>(cur, oth, N, Nz, Nx * Ny, twz);
+        __syncthreads();
+        double2 *t = cur; cur = oth; oth = t;
+    }
+
+    // ---- level n: periodic coefficients (real part) -> device level format
+    const ExpandParams &E = S.E;
+    if (E.dim == 1) {
+        for (int i = threadIdx.x; i < Nx + 3; i += blockDim.x) S.raw1d[i] = cur[i % Nx].x;
+        for (int k = threadIdx.x; k < Nx; k += blockDim.x) {
+            double c[4], p0, p1, p2;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) c[a] = cur[(k + a) % Nx].x;
+            cell_poly_1d(c, E.g1, p0, p1, p2);
+            S.level[3 * k] = p0;
+            S.level[3 * k + 1] = p1;
+            S.level[3 * k + 2] = p2;
+        }
+        if (threadIdx.x == 0 && (3 * Nx) % 2) S.level[3 * Nx] = 0;
+    } else {
+        const int rows = Ny + 3;
+        for (size_t idx = threadIdx.x; idx < E.level_doubles; idx += blockDim.x) {
+            const int i = static_cast<int>(idx % E.sx);
+            const size_t rest = idx / E.sx;
+            const int j = static_cast<int>(rest % rows);
+            const int k = static_cast<int>(rest / rows);
+            double v = 0;
+            if (i < Nx + 3 && (E.dim < 3 ? k == 0 : k < Nz + 3)) v = cur[((k % Nz) * Ny + (j % Ny)) * Nx + (i % Nx)].x;
+            S.level[idx] = v;
+        }
+    }
+}
+
 ExpandParams expand_params(const Handle *h)
 {
     ExpandParams E{};
     E.dim = h->dim;
     E.Nx = static_cast<int>(h->c.Nx); E.Ny = static_cast<int>(h->c.Ny); E.Nz = static_cast<int>(h->c.Nz);
-    E.sx = h->sx; E.sxy = h->sxy; E.Nxp = h->Nxp;
+    E.sx = h->sx; E.sxy = h->sxy;
     E.level_doubles = h->level_stride;
     E.g1 = -h->c.dt * h->c.dx_inv;
     return E;
@@ -263,6 +447,18 @@ int tail_init(Handle *h)
     }
     NUFI_CUDA_CHECK(h, cudaMalloc(&h->d_symbol, tab.size() * sizeof(double)));
     NUFI_CUDA_CHECK(h, cudaMemcpy(h->d_symbol, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    {   // exact twiddles for the fused small-grid tail: (cos, sin)(2 pi m / N_d), the three tables back to back
+        std::vector<double> tw(2 * (static_cast<size_t>(Nx) + Ny + Nz));
+        size_t o = 0;
+        for (int d = 0; d < 3; ++d)
+            for (int m = 0; m < Ns[d]; ++m, ++o) {
+                const double th = 2 * M_PI * static_cast<double>(m) / Ns[d];
+                tw[2 * o] = std::cos(th);
+                tw[2 * o + 1] = std::sin(th);
+            }
+        NUFI_CUDA_CHECK(h, cudaMalloc(&h->d_twiddle, tw.size() * sizeof(double)));
+        NUFI_CUDA_CHECK(h, cudaMemcpy(h->d_twiddle, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     NUFI_CUDA_CHECK(h, cudaMalloc(&h->d_spec, h->n_spec * sizeof(cufftDoubleComplex)));
     NUFI_CUDA_CHECK(h, cudaMalloc(&h->d_field, h->n_nodes * sizeof(double)));
     NUFI_CUDA_CHECK(h, cudaMalloc(&h->d_epart, kSymbolBlocks * sizeof(double)));
@@ -277,22 +473,27 @@ void tail_destroy(Handle *h)
         h->plans = false;
     }
     cudaFree(h->d_symbol);
+    cudaFree(h->d_twiddle);
+    h->d_twiddle = nullptr;
     cudaFree(h->d_spec);
     cudaFree(h->d_field);
     cudaFree(h->d_epart);
     h->d_symbol = nullptr; h->d_spec = nullptr; h->d_field = nullptr; h->d_epart = nullptr;
 }
 
-// rho (CPU convention, device) -> level n in the device history + energy[n]
+static bool small_tail_ok(const Handle *h)
+{
+    return h->n_nodes <= static_cast<size_t>(kSmallMaxNodes) && h->c.Nx <= kSmallMaxDim && h->c.Ny <= kSmallMaxDim &&
+           h->c.Nz <= kSmallMaxDim;
+}
+
+// rho (CPU convention, device) -> level n in the device history + energy[n].
+// d_rho_full == nullptr: rho comes from the pending slot reduction of the last backtrace launch (fused step).
 int tail_run(Handle *h, size_t n, const double *d_rho_full)
 {
     const nufi_b200_config3d &c = h->c;
-    if (cufftSetStream(h->plan_fwd, h->stream) != CUFFT_SUCCESS || cufftSetStream(h->plan_inv, h->stream) != CUFFT_SUCCESS)
-        return fail(h, NUFI_B200_ERR_CUDA, "cufftSetStream failed");
-    // cuFFT's D2Z may overwrite nothing of its input (out-of-place), Z2D may overwrite its input (d_spec: fine)
-    if (cufftExecD2Z(h->plan_fwd, const_cast<double *>(d_rho_full), h->d_spec) != CUFFT_SUCCESS)
-        return fail(h, NUFI_B200_ERR_CUDA, "cufftExecD2Z failed");
     TailParams T{};
+    T.dim = h->dim;
     T.Nx = static_cast<int>(c.Nx); T.Ny = static_cast<int>(c.Ny); T.Nz = static_cast<int>(c.Nz);
     T.Nxh = T.Nx / 2 + 1;
     const size_t nt = (c.Nx + c.Ny + c.Nz + 1) & ~size_t(1);
@@ -303,15 +504,58 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full)
     if (h->dim >= 2) vol_half = c.Lx * c.Ly;
     if (h->dim >= 3) vol_half = c.Lx * c.Ly * c.Lz;
     vol_half = vol_half / 2;
+    T.vol_half = vol_half;
+    ExpandParams E = expand_params(h);
+    double *level = h->d_hist + n * h->level_stride;
+
+    const bool small = h->tail_force == 2 || (h->tail_force == 0 && small_tail_ok(h));
+    if (small) {
+        if (!small_tail_ok(h)) return fail(h, NUFI_B200_ERR_ARG, "fused single-CTA tail forced but the grid is too large for it");
+        SmallTailParams S{};
+        S.T = T; S.E = E;
+        S.twx = reinterpret_cast<const double2 *>(h->d_twiddle); S.twy = S.twx + c.Nx; S.twz = S.twy + c.Ny;
+        S.level = level;
+        S.raw1d = h->dim == 1 ? h->d_raw + n * h->raw_stride : nullptr;
+        S.energy_out = h->d_energy + n;
+        if (d_rho_full) {
+            S.rho = d_rho_full;
+        } else {
+            if (!h->fin_pending) return fail(h, NUFI_B200_ERR_ARG, "field tail: no rho on the device");
+            S.rho = nullptr;
+            S.F = h->fin;
+            h->fin_pending = false;
+        }
+        const size_t smem = (2 * h->n_nodes + c.Nx + c.Ny + c.Nz) * sizeof(double2);
+        if (smem > 48 * 1024)
+            NUFI_CUDA_CHECK(h, cudaFuncSetAttribute(tail_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        unsigned threads = static_cast<unsigned>((h->n_nodes + 31) / 32 * 32);
+        if (threads > kSmallThreads) threads = kSmallThreads;
+        if (threads < 128) threads = 128;
+        tail_small_kernel<<<1, threads, smem, h->stream>>>(S);
+        NUFI_CUDA_CHECK(h, cudaGetLastError());
+        h->launches += 1;
+        h->last_tail = "fused-1cta";
+        h->level_valid[n] = 1;
+        return NUFI_B200_OK;
+    }
+
+    if (!d_rho_full) { // the cuFFT path reads rho from memory: run the slot reduction first
+        int rc = launch_finish(h);
+        if (rc) return rc;
+        d_rho_full = h->d_rho_full;
+    }
+    if (cufftSetStream(h->plan_fwd, h->stream) != CUFFT_SUCCESS || cufftSetStream(h->plan_inv, h->stream) != CUFFT_SUCCESS)
+        return fail(h, NUFI_B200_ERR_CUDA, "cufftSetStream failed");
+    // cuFFT's D2Z may overwrite nothing of its input (out-of-place), Z2D may overwrite its input (d_spec: fine)
+    if (cufftExecD2Z(h->plan_fwd, const_cast<double *>(d_rho_full), h->d_spec) != CUFFT_SUCCESS)
+        return fail(h, NUFI_B200_ERR_CUDA, "cufftExecD2Z failed");
     const unsigned sblocks = blocks_for(h->n_spec, 256, kSymbolBlocks);
     symbol_kernel<<<sblocks, 256, 0, h->stream>>>(h->d_spec, T, h->d_epart);
     NUFI_CUDA_CHECK(h, cudaGetLastError());
     if (cufftExecZ2D(h->plan_inv, h->d_spec, h->d_field) != CUFFT_SUCCESS)
         return fail(h, NUFI_B200_ERR_CUDA, "cufftExecZ2D failed");
-    ExpandParams E = expand_params(h);
-    double *level = h->d_hist + n * h->level_stride;
     if (h->dim == 1) {
-        expand1d_kernel<<<blocks_for(h->Nxp, 256, 64), 256, 0, h->stream>>>(h->d_field, h->d_raw + n * h->raw_stride, level, E,
+        expand1d_kernel<<<blocks_for(c.Nx + 3, 256, 64), 256, 0, h->stream>>>(h->d_field, h->d_raw + n * h->raw_stride, level, E,
                                                                           h->d_epart, sblocks, vol_half, h->d_energy + n);
     } else {
         expand_kernel<<<blocks_for(h->level_stride, 256, 1184), 256, 0, h->stream>>>(h->d_field, level, E, 0.0, h->d_epart, sblocks,
@@ -319,6 +563,7 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full)
     }
     NUFI_CUDA_CHECK(h, cudaGetLastError());
     h->launches += 4; // D2Z, symbol, Z2D, expand (cuFFT may use more than one kernel per transform)
+    h->last_tail = "cufft";
     h->level_valid[n] = 1;
     return NUFI_B200_OK;
 }

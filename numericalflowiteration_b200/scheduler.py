@@ -188,6 +188,14 @@ class CudaScheduler:
     def set_variant(self, v: int) -> None:
         self._ck(self._L.nufi_b200_set_variant(self._h, v))
 
+    def set_tail_variant(self, v: int) -> None:
+        """0 auto, 1 cuFFT tail, 2 fused single-CTA tail."""
+        self._ck(self._L.nufi_b200_set_tail_variant(self._h, v))
+
+    @property
+    def last_tail_variant(self) -> str:
+        return self._L.nufi_b200_last_tail_variant(self._h).decode()
+
 
 def measure_fp64_peak(device: int = -1) -> float:
     """Register-only DFMA loop: measured FP64 peak of the device in TFLOP/s."""

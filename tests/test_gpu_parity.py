@@ -69,8 +69,9 @@ def test_partial_ranges_accumulate(name, histories, oracle):
         assert rel_linf(1.0 + total, want) <= RHO_TOL
 
 
+@pytest.mark.parametrize("tail", [1, 2], ids=["cufft", "fused-1cta"])
 @pytest.mark.parametrize("name", ["1d-landau", "2d-landau", "3d-landau", "3d-bump"])
-def test_field_tail(name, histories, oracle):
+def test_field_tail(name, tail, histories, oracle):
     """solve + interpolate on the device vs poisson.cpp / fields.hpp restated (and LSMR via oracle/_ref in
     test_oracle_vs_ref): coefficients and electric energy."""
     conf, f0, coeffs, _ = histories[name]
@@ -79,17 +80,21 @@ def test_field_tail(name, histories, oracle):
     phi, e_want = oracle.poisson(conf, rho)
     level_want = oracle.interpolate(conf, phi)
     with CudaScheduler(conf, f0) as s:
+        s.set_tail_variant(tail)
         e_got = s.solve_interpolate(n, rho=rho)
         level_got = s.download_phi(n)
+        assert s.last_tail_variant == ("cufft" if tail == 1 else "fused-1cta")
     assert abs(e_got - e_want) <= 1e-12 * abs(e_want)
     assert rel_linf(level_got, level_want) <= COEFF_TOL
 
 
+@pytest.mark.parametrize("tail", [0, 1], ids=["tail-auto", "tail-cufft"])
 @pytest.mark.parametrize("name", ["1d-two-stream", "1d-landau", "2d-landau", "3d-landau", "3d-bump"])
-def test_free_run_energy_trace(name, histories):
+def test_free_run_energy_trace(name, tail, histories):
     """The fused step() loop, no host round trip, against the reference CPU loop."""
     conf, f0, coeffs, energy = histories[name]
     with CudaScheduler(conf, f0) as s:
+        s.set_tail_variant(tail)
         for n in range(conf.Nt):
             s.step(n)
         got = s.download_energy(0, conf.Nt)
@@ -145,3 +150,33 @@ def test_run_to_run_deterministic(histories):
         a = s.eval_rho(conf.Nt)
         b = s.eval_rho(conf.Nt)
     assert np.array_equal(a, b)
+
+
+def test_multi_round_ragged_tiles(oracle):
+    """More CTA-rounds than SMs (several rounds per CTA, tile changes inside a CTA), tiles that straddle grid rows
+    (Nx = 40), a last tile that is only partly filled, non-power-of-two periodic wrap."""
+    conf = conf2d(Nx=40, Ny=25, Nu=20, Nv=12, Nt=8)
+    f0 = F0(0, 0.05, 0.5)
+    coeffs, _, _ = oracle.run(conf, f0, conf.Nt)
+    with CudaScheduler(conf, f0) as s:
+        s.upload_history(coeffs, conf.Nt)
+        for variant in (1, 2):
+            s.set_variant(variant)
+            got = s.eval_rho(conf.Nt)
+            assert rel_linf(got, oracle.rho(conf, f0, conf.Nt, coeffs)) <= RHO_TOL, s.last_variant
+
+
+@pytest.mark.parametrize("nx", [12, 16])
+def test_multi_period_jump_in_one_step(nx, oracle):
+    """A point that crosses more than one whole period in a single drift (dt*|u|/dx > Nx).  Power-of-two grids wrap by
+    masking; other grids clamp, flag and redo the point on the robust path -- both must agree with the reference's
+    floor()-based wrap."""
+    conf = conf1d(Nx=nx, Nu=64, Nt=6, dt=4.0, u_min=-6.0, u_max=6.0)  # |u| ~ 4 carries weight and jumps > Lx
+    f0 = F0(0, 0.01, 0.5)
+    coeffs, _, _ = oracle.run(conf, f0, conf.Nt)
+    assert conf.dt * 4.0 / conf.dx > conf.Nx
+    with CudaScheduler(conf, f0) as s:
+        s.upload_history(coeffs, conf.Nt)
+        for n in (1, 3, conf.Nt):
+            got = s.eval_rho(n)
+            assert rel_linf(got, oracle.rho(conf, f0, n, coeffs)) <= RHO_TOL, (nx, n)
