@@ -1,0 +1,8 @@
+// bin/test_nufi_cpu_2d -- the reference's CPU driver loop (bin/test_nufi_cpu_2d.cpp) with eval_rho / solve / interpolate
+// served by libnufi_b200; see nufi_drivers.hpp.
+#include "nufi_drivers.hpp"
+
+int main(int argc, char *argv[])
+{
+    return nufi_drivers::guarded([&] { return nufi_drivers::cpu_main<2>(argc, argv); });
+}

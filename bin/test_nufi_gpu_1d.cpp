@@ -1,0 +1,7 @@
+// bin/test_nufi_gpu_1d -- the reference's GPU driver loop (bin/test_nufi_gpu_1d.cpp) on libnufi_b200; see nufi_drivers.hpp.
+#include "nufi_drivers.hpp"
+
+int main(int argc, char *argv[])
+{
+    return nufi_drivers::guarded([&] { return nufi_drivers::gpu_main<1>(argc, argv); });
+}

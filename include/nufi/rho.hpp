@@ -1,0 +1,39 @@
+// nufi/rho.hpp -- eval_rho with the reference's signature (nufi/rho.hpp:133-134, 283-284, 428-429), computed on the GPU.
+//
+// The reference's CPU drivers call  rho[l] = eval_rho<real,order>(n, l, coeffs, conf)  for every spatial node l inside an
+// OpenMP loop (bin/test_nufi_cpu_1d.cpp:65-70, _2d.cpp:68-72, _3d.cpp:68-72).  Here the FIRST call for a step n runs the
+// whole sweep on the device in one launch (after pushing the levels of `coeffs` the device does not hold yet) and every
+// call, from any thread, returns its node from that result -- so the driver loop compiles and runs unchanged.
+// eval_rho_all is the same thing without the per-node detour.
+#ifndef NUFI_B200_NUFI_RHO_HPP
+#define NUFI_B200_NUFI_RHO_HPP
+
+#include "device_context.hpp"
+
+namespace nufi
+{
+
+#define NUFI_B200_DEFINE_RHO(DIM)                                                                                       \
+    namespace DIM                                                                                                       \
+    {                                                                                                                   \
+    template <typename real, size_t order> real eval_rho(size_t n, size_t l, const real *coeffs, const config_t<real> &conf) \
+    {                                                                                                                   \
+        static_assert(std::is_same<real, double>::value, "libnufi_b200 computes in FP64");                              \
+        return detail::context<config_t<real>, order>(conf).rho(n, coeffs)[l];                                          \
+    }                                                                                                                   \
+    template <typename real, size_t order> void eval_rho_all(size_t n, real *rho, const real *coeffs, const config_t<real> &conf) \
+    {                                                                                                                   \
+        static_assert(std::is_same<real, double>::value, "libnufi_b200 computes in FP64");                              \
+        const std::vector<double> &r = detail::context<config_t<real>, order>(conf).rho(n, coeffs);                     \
+        std::memcpy(rho, r.data(), sizeof(double) * r.size());                                                          \
+    }                                                                                                                   \
+    }
+
+NUFI_B200_DEFINE_RHO(dim1)
+NUFI_B200_DEFINE_RHO(dim2)
+NUFI_B200_DEFINE_RHO(dim3)
+#undef NUFI_B200_DEFINE_RHO
+
+} // namespace nufi
+
+#endif

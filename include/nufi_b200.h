@@ -129,6 +129,14 @@ int nufi_b200_solve_interpolate(nufi_b200_handle *h, size_t n, double *energy);
 /* same, but from a host rho (CPU convention), e.g. after an MPI/host reduction; blocking */
 int nufi_b200_solve_interpolate_host(nufi_b200_handle *h, size_t n, const double *rho_host, double *energy);
 
+/* dimN::poisson<double>::solve alone (nufi/poisson.cpp:66-89, 190-219, 328-362): data (Nx*Ny*Nz nodal values of rho, host)
+ * is overwritten with phi at the nodes; *energy (may be NULL) = the returned electric energy.  Blocking. */
+int nufi_b200_poisson_solve(nufi_b200_handle *h, double *data_host, double *energy);
+/* dimN::interpolate<double,4> alone (nufi/fields.hpp:63-142, 186-300, 352-490): nodal values (host) -> one level of
+ * coefficients with the (order-1) periodic halo, reference layout, stride_t doubles (host).  Blocking; the device history
+ * is not touched (push the level with nufi_b200_upload_phi as the reference loop does). */
+int nufi_b200_interpolate(nufi_b200_handle *h, const double *values_host, double *coeffs_level_host);
+
 /* ---- fused step: backtrace + reduce + Poisson + interpolate + store level n, no host round trip.
  *      Asynchronous; the electric energy of step n is kept on the device (nufi_b200_download_energy). ---- */
 int nufi_b200_step(nufi_b200_handle *h, size_t n);
@@ -147,7 +155,24 @@ int nufi_b200_rho_device(nufi_b200_handle *h, double **d_rho);
  * rho = 1 + sum, solve, interpolate, store level n, record energy[n].  Asynchronous. */
 int nufi_b200_field_tail_device(nufi_b200_handle *h, size_t n, const double *d_rho_partial_sum);
 
+/* ---- several GPUs driven by ONE process (the reference's cuda_scheduler shape: one host thread, all visible devices,
+ *      nufi/cuda_scheduler.hpp:43-63).  A group ties one handle per device together with NCCL communicators
+ *      (ncclCommInitAll; libnccl.so.2 is loaded on first use).  group_step = per device: backtrace of its contiguous
+ *      share of the flat q range (the reference's split, cuda_scheduler.hpp:88-111) -> ncclAllReduce(sum) of the
+ *      partial rho in place on the devices (replaces download_rho + host add + MPI_Allreduce,
+ *      bin/test_nufi_gpu_3d.cpp:154-158) -> the replicated field tail on every device.  Asynchronous. ---- */
+typedef struct nufi_b200_group nufi_b200_group;
+int nufi_b200_group_create(nufi_b200_handle *const *handles, int n_handles, nufi_b200_group **out);
+void nufi_b200_group_destroy(nufi_b200_group *g);
+int nufi_b200_group_step(nufi_b200_group *g, size_t n);
+int nufi_b200_group_sync(nufi_b200_group *g);
+const char *nufi_b200_group_last_error(const nufi_b200_group *g);
+
 /* ---- introspection used by bench.py / tests ---- */
+/* number of visible CUDA devices (cuda::device_count, nufi/cuda_runtime.hpp:196-203) */
+int nufi_b200_device_count(int *count);
+/* device index a handle lives on (-1 for NULL) */
+int nufi_b200_device_of(const nufi_b200_handle *h);
 /* number of kernels this library launched on h since creation */
 uint64_t nufi_b200_launch_count(const nufi_b200_handle *h);
 /* GPU time in ms of the most recent backtrace kernel (CUDA events on the launching stream); blocking */

@@ -7,10 +7,10 @@ library ``lib/libnufi_b200.so`` (``include/nufi_b200.h``); this package is its h
 reference's ``config_t`` / ``cuda_scheduler`` interface.  There is no CPU fallback.
 """
 from .config import Config1D, Config2D, Config3D, F0, n_nodes, n_quad, n_vel, stride_t
-from .scheduler import CudaError, CudaScheduler, RangeError, measure_fp64_peak
+from .scheduler import CudaError, CudaGroup, CudaScheduler, RangeError, device_count, measure_fp64_peak
 from .distributed import partition, DistributedStepper
 
 __all__ = [
     "Config1D", "Config2D", "Config3D", "F0", "n_nodes", "n_quad", "n_vel", "stride_t",
-    "CudaScheduler", "CudaError", "RangeError", "measure_fp64_peak", "partition", "DistributedStepper",
+    "CudaScheduler", "CudaGroup", "device_count", "CudaError", "RangeError", "measure_fp64_peak", "partition", "DistributedStepper",
 ]

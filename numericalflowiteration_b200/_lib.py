@@ -16,10 +16,12 @@ SYMBOLS = [
     "nufi_b200_create_1d", "nufi_b200_create_2d", "nufi_b200_create_3d", "nufi_b200_destroy", "nufi_b200_last_error",
     "nufi_b200_compute_rho", "nufi_b200_download_rho", "nufi_b200_upload_phi", "nufi_b200_compute_metrics",
     "nufi_b200_download_metrics", "nufi_b200_eval_rho_all", "nufi_b200_solve_interpolate",
-    "nufi_b200_solve_interpolate_host", "nufi_b200_step", "nufi_b200_download_energy", "nufi_b200_download_phi",
+    "nufi_b200_solve_interpolate_host", "nufi_b200_poisson_solve", "nufi_b200_interpolate", "nufi_b200_step", "nufi_b200_download_energy", "nufi_b200_download_phi",
     "nufi_b200_sync", "nufi_b200_set_stream", "nufi_b200_rho_device", "nufi_b200_field_tail_device",
     "nufi_b200_launch_count", "nufi_b200_last_backtrace_ms", "nufi_b200_backtrace_time", "nufi_b200_last_variant", "nufi_b200_set_variant",
     "nufi_b200_set_tail_variant", "nufi_b200_last_tail_variant", "nufi_b200_measure_fp64_peak", "nufi_b200_version",
+    "nufi_b200_group_create", "nufi_b200_group_destroy", "nufi_b200_group_step", "nufi_b200_group_sync",
+    "nufi_b200_group_last_error", "nufi_b200_device_count", "nufi_b200_device_of",
 ]
 
 _lib = None
@@ -58,6 +60,8 @@ def load() -> C.CDLL:
         "rho_device": [vp, C.POINTER(vp)], "field_tail_device": [vp, sz, vp], "last_backtrace_ms": [vp, C.POINTER(C.c_float)],
         "set_variant": [vp, i], "measure_fp64_peak": [i, dp],
         "backtrace_time": [vp, dp, C.POINTER(C.c_uint64), i], "set_tail_variant": [vp, i],
+        "poisson_solve": [vp, vp, dp], "interpolate": [vp, vp, vp], "device_count": [C.POINTER(i)], "device_of": [vp],
+        "group_create": [C.POINTER(vp), i, C.POINTER(vp)], "group_step": [vp, sz], "group_sync": [vp],
     }.items():
         f = getattr(L, "nufi_b200_" + name)
         f.argtypes = args
@@ -68,6 +72,10 @@ def load() -> C.CDLL:
     L.nufi_b200_last_variant.restype = C.c_char_p
     L.nufi_b200_last_tail_variant.argtypes = [vp]
     L.nufi_b200_last_tail_variant.restype = C.c_char_p
+    L.nufi_b200_group_destroy.argtypes = [vp]
+    L.nufi_b200_group_destroy.restype = None
+    L.nufi_b200_group_last_error.argtypes = [vp]
+    L.nufi_b200_group_last_error.restype = C.c_char_p
     L.nufi_b200_version.restype = C.c_char_p
     _lib = L
     return L

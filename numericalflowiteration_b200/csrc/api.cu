@@ -334,6 +334,43 @@ int nufi_b200_solve_interpolate_host(nufi_b200_handle *h, size_t n, const double
     return NUFI_B200_OK;
 }
 
+int nufi_b200_poisson_solve(nufi_b200_handle *h, double *data_host, double *energy)
+{
+    ENTER(h);
+    if (!data_host) return fail(hh, NUFI_B200_ERR_ARG, "data is NULL");
+    std::memcpy(hh->h_pinned, data_host, sizeof(double) * hh->n_nodes);
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(hh->d_rho_full, hh->h_pinned, sizeof(double) * hh->n_nodes, cudaMemcpyHostToDevice, hh->stream));
+    int rc = tail_filter(hh, hh->d_rho_full, 1);
+    if (rc) return rc;
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream)); // h_pinned is reused for the way back
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(hh->h_pinned, hh->d_field, sizeof(double) * hh->n_nodes, cudaMemcpyDeviceToHost, hh->stream));
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    std::memcpy(data_host, hh->h_pinned, sizeof(double) * hh->n_nodes);
+    if (energy) {
+        NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(hh->h_pinned, tail_energy_scratch(hh), sizeof(double), cudaMemcpyDeviceToHost, hh->stream));
+        NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+        *energy = hh->h_pinned[0];
+    }
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_interpolate(nufi_b200_handle *h, const double *values_host, double *coeffs_level_host)
+{
+    ENTER(h);
+    if (!values_host || !coeffs_level_host) return fail(hh, NUFI_B200_ERR_ARG, "values / coeffs is NULL");
+    std::memcpy(hh->h_pinned, values_host, sizeof(double) * hh->n_nodes);
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(hh->d_rho_full, hh->h_pinned, sizeof(double) * hh->n_nodes, cudaMemcpyHostToDevice, hh->stream));
+    int rc = tail_filter(hh, hh->d_rho_full, 2);
+    if (rc) return rc;
+    rc = expand_field_to_stage(hh);
+    if (rc) return rc;
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(hh->h_pinned, hh->d_stage, sizeof(double) * hh->stride_t, cudaMemcpyDeviceToHost, hh->stream));
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    std::memcpy(coeffs_level_host, hh->h_pinned, sizeof(double) * hh->stride_t);
+    return NUFI_B200_OK;
+}
+
 int nufi_b200_step(nufi_b200_handle *h, size_t n)
 {
     ENTER(h);
@@ -457,6 +494,20 @@ int nufi_b200_set_tail_variant(nufi_b200_handle *h, int variant)
 const char *nufi_b200_last_tail_variant(const nufi_b200_handle *h) { return h ? H(h)->last_tail : "none"; }
 
 int nufi_b200_measure_fp64_peak(int device, double *tflops) { return measure_fp64_peak(device, tflops); }
+
+int nufi_b200_device_count(int *count)
+{
+    if (!count) return fail(nullptr, NUFI_B200_ERR_ARG, "count is NULL");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(nullptr, NUFI_B200_ERR_CUDA, std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e));
+    }
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_device_of(const nufi_b200_handle *h) { return h ? H(h)->device : -1; }
 
 const char *nufi_b200_version(void) { return "nufi_b200 0.1 (sm_100a)"; }
 

@@ -136,6 +136,9 @@ int tail_init(Handle *h);
 void tail_destroy(Handle *h);
 // d_rho_full == nullptr: take rho from the pending slot reduction of the last backtrace launch
 int tail_run(Handle *h, size_t n, const double *d_rho_full);
+int tail_filter(Handle *h, const double *d_values, int mode); // 1: poisson solve, 2: interpolate; result in d_field
+int expand_field_to_stage(Handle *h);
+double *tail_energy_scratch(Handle *h);
 int convert_level_to_device(Handle *h, size_t n, const double *d_ref_level);  // reference format -> device format
 int convert_level_from_device(Handle *h, size_t n, double *d_ref_level);      // device format -> reference format
 int make_full_rho(Handle *h, const double *d_partial_sum, double *d_full);    // full = 1 + partial

@@ -26,6 +26,7 @@ struct TailParams
     const double2 *ilx, *ily, *ilz;      // per-dimension 1/lambda
     double fac_N;                   // 1/(Nx Ny Nz)
     double vol_half;                // Lx Ly Lz / 2
+    int mode;                       // bit 0: Poisson symbol 1/|kappa|^2 (zero mean mode), bit 1: collocation symbol 1/lambda
 };
 
 // spec <- spec * symbol;  per-block partial of sum_k w_k |kappa|^2 |phi^_k|^2  (w = 1 on the self-conjugate
@@ -42,15 +43,24 @@ __global__ void symbol_kernel(cufftDoubleComplex *spec, TailParams T, double *ep
         const int ky = static_cast<int>(rest % T.Ny);
         const int kz = static_cast<int>(rest / T.Ny);
         cufftDoubleComplex F = spec[idx];
-        if (kx == 0 && ky == 0 && kz == 0) {
-            spec[idx] = make_cuDoubleComplex(0.0, 0.0); // data[0] = 0 (poisson.cpp:83, 214, 357)
+        double pr, pi;
+        if (T.mode & 1) {
+            if (kx == 0 && ky == 0 && kz == 0) {
+                spec[idx] = make_cuDoubleComplex(0.0, 0.0); // data[0] = 0 (poisson.cpp:83, 214, 357)
+                continue;
+            }
+            const double kap2 = T.kap2x[kx] + T.kap2y[ky] + T.kap2z[kz];
+            const double fac = T.fac_N / kap2;
+            pr = F.x * fac; pi = F.y * fac; // phi^_k / N-normalised
+            const double w = (kx == 0 || 2 * kx == T.Nx) ? 1.0 : 2.0;
+            e += w * kap2 * (pr * pr + pi * pi);
+        } else {
+            pr = F.x * T.fac_N; pi = F.y * T.fac_N;
+        }
+        if (!(T.mode & 2)) {
+            spec[idx] = make_cuDoubleComplex(pr, pi);
             continue;
         }
-        const double kap2 = T.kap2x[kx] + T.kap2y[ky] + T.kap2z[kz];
-        const double fac = T.fac_N / kap2;
-        const double pr = F.x * fac, pi = F.y * fac; // phi^_k / N-normalised
-        const double w = (kx == 0 || 2 * kx == T.Nx) ? 1.0 : 2.0;
-        e += w * kap2 * (pr * pr + pi * pi);
         // divide by the collocation symbol, dimension by dimension
         double2 a = T.ilx[kx];
         double2 b = T.ily[ky];
@@ -461,7 +471,7 @@ int tail_init(Handle *h)
     }
     NUFI_CUDA_CHECK(h, cudaMalloc(&h->d_spec, h->n_spec * sizeof(cufftDoubleComplex)));
     NUFI_CUDA_CHECK(h, cudaMalloc(&h->d_field, h->n_nodes * sizeof(double)));
-    NUFI_CUDA_CHECK(h, cudaMalloc(&h->d_epart, kSymbolBlocks * sizeof(double)));
+    NUFI_CUDA_CHECK(h, cudaMalloc(&h->d_epart, (kSymbolBlocks + 1) * sizeof(double)));
     return NUFI_B200_OK;
 }
 
@@ -505,6 +515,7 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full)
     if (h->dim >= 3) vol_half = c.Lx * c.Ly * c.Lz;
     vol_half = vol_half / 2;
     T.vol_half = vol_half;
+    T.mode = 3;
     ExpandParams E = expand_params(h);
     double *level = h->d_hist + n * h->level_stride;
 
@@ -567,6 +578,75 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full)
     h->level_valid[n] = 1;
     return NUFI_B200_OK;
 }
+
+// Reference-format level (halo, row stride Nx+3) from periodic coefficients; 1 thread per output element.
+__global__ void expand_ref_kernel(const double *src, double *ref, int dim, int Nx, int Ny, int Nz)
+{
+    const int rx = Nx + 3, ry = dim >= 2 ? Ny + 3 : 1, rz = dim >= 3 ? Nz + 3 : 1;
+    const size_t total = static_cast<size_t>(rx) * ry * rz;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int i = static_cast<int>(idx % rx);
+        const size_t rest = idx / rx;
+        const int j = static_cast<int>(rest % ry);
+        const int k = static_cast<int>(rest / ry);
+        ref[idx] = src[(static_cast<size_t>(k % Nz) * Ny + (j % Ny)) * Nx + (i % Nx)];
+    }
+}
+
+__global__ void sum_epart_kernel(const double *epart, unsigned n, double vol_half, double *out)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double s = 0;
+        for (unsigned b = 0; b < n; ++b) s += epart[b];
+        *out = s * vol_half;
+    }
+}
+
+// Spectral filter on a device vector of nodal values: mode 1 = poisson::solve (phi at the nodes + energy),
+// mode 2 = interpolate (periodic coefficients).  Result in h->d_field; energy (mode 1) in h->d_epart[kSymbolBlocks].
+int tail_filter(Handle *h, const double *d_values, int mode)
+{
+    const nufi_b200_config3d &c = h->c;
+    TailParams T{};
+    T.dim = h->dim;
+    T.Nx = static_cast<int>(c.Nx); T.Ny = static_cast<int>(c.Ny); T.Nz = static_cast<int>(c.Nz);
+    T.Nxh = T.Nx / 2 + 1;
+    const size_t nt = (c.Nx + c.Ny + c.Nz + 1) & ~size_t(1);
+    T.kap2x = h->d_symbol; T.kap2y = T.kap2x + c.Nx; T.kap2z = T.kap2y + c.Ny;
+    T.ilx = reinterpret_cast<const double2 *>(h->d_symbol + nt); T.ily = T.ilx + c.Nx; T.ilz = T.ily + c.Ny;
+    T.fac_N = 1.0 / static_cast<double>(c.Nx * c.Ny * c.Nz);
+    double vol_half = c.Lx;
+    if (h->dim >= 2) vol_half = c.Lx * c.Ly;
+    if (h->dim >= 3) vol_half = c.Lx * c.Ly * c.Lz;
+    T.vol_half = vol_half / 2;
+    T.mode = mode;
+    if (cufftSetStream(h->plan_fwd, h->stream) != CUFFT_SUCCESS || cufftSetStream(h->plan_inv, h->stream) != CUFFT_SUCCESS)
+        return fail(h, NUFI_B200_ERR_CUDA, "cufftSetStream failed");
+    if (cufftExecD2Z(h->plan_fwd, const_cast<double *>(d_values), h->d_spec) != CUFFT_SUCCESS)
+        return fail(h, NUFI_B200_ERR_CUDA, "cufftExecD2Z failed");
+    const unsigned sblocks = blocks_for(h->n_spec, 256, kSymbolBlocks);
+    symbol_kernel<<<sblocks, 256, 0, h->stream>>>(h->d_spec, T, h->d_epart);
+    NUFI_CUDA_CHECK(h, cudaGetLastError());
+    if (cufftExecZ2D(h->plan_inv, h->d_spec, h->d_field) != CUFFT_SUCCESS)
+        return fail(h, NUFI_B200_ERR_CUDA, "cufftExecZ2D failed");
+    sum_epart_kernel<<<1, 32, 0, h->stream>>>(h->d_epart, sblocks, T.vol_half, h->d_epart + kSymbolBlocks);
+    NUFI_CUDA_CHECK(h, cudaGetLastError());
+    h->launches += 4;
+    return NUFI_B200_OK;
+}
+
+// periodic coefficients in h->d_field -> reference-format level in h->d_stage
+int expand_field_to_stage(Handle *h)
+{
+    expand_ref_kernel<<<blocks_for(h->stride_t, 256, 1184), 256, 0, h->stream>>>(h->d_field, h->d_stage, h->dim, static_cast<int>(h->c.Nx),
+                                                                               static_cast<int>(h->c.Ny), static_cast<int>(h->c.Nz));
+    NUFI_CUDA_CHECK(h, cudaGetLastError());
+    h->launches += 1;
+    return NUFI_B200_OK;
+}
+
+double *tail_energy_scratch(Handle *h) { return h->d_epart + kSymbolBlocks; }
 
 int convert_level_to_device(Handle *h, size_t n, const double *d_ref_level)
 {

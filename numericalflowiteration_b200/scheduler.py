@@ -19,7 +19,7 @@ import numpy as np
 from . import _lib
 from .config import F0, n_nodes, n_quad, stride_t
 
-__all__ = ["CudaScheduler", "CudaError", "RangeError", "measure_fp64_peak"]
+__all__ = ["CudaScheduler", "CudaGroup", "CudaError", "RangeError", "measure_fp64_peak", "device_count"]
 
 
 class CudaError(RuntimeError):
@@ -205,3 +205,60 @@ def measure_fp64_peak(device: int = -1) -> float:
     if rc != _lib.OK:
         _raise(rc, L.nufi_b200_last_error(None).decode())
     return t.value
+
+
+def device_count() -> int:
+    """Visible CUDA devices (cuda::device_count in the reference); raises CudaError without a driver."""
+    L = _lib.load()
+    n = C.c_int(0)
+    rc = L.nufi_b200_device_count(C.byref(n))
+    if rc != _lib.OK:
+        _raise(rc, L.nufi_b200_last_error(None).decode())
+    return n.value
+
+
+class CudaGroup:
+    """Several GPUs driven by ONE process -- the shape of the reference's ``cuda_scheduler`` (one host thread, all visible
+    devices, nufi/cuda_scheduler.hpp:43-63) with the host fan-in replaced by an NCCL all-reduce on the devices.
+    ``step(n)``: every device traces its contiguous share of the flat q range, the partial rho vectors are summed in
+    place over NVLink, every device runs the (tiny, deterministic) field tail."""
+
+    def __init__(self, conf, f0: F0 | None = None, devices=None, order: int = 4):
+        self._L = _lib.load()
+        devices = list(range(device_count())) if devices is None else list(devices)
+        self.scheds = [CudaScheduler(conf, f0, order=order, device=d) for d in devices]
+        arr = (C.c_void_p * len(self.scheds))(*[s._h for s in self.scheds])
+        self._g = C.c_void_p()
+        rc = self._L.nufi_b200_group_create(arr, len(self.scheds), C.byref(self._g))
+        if rc != _lib.OK:
+            self._g = C.c_void_p()
+            _raise(rc, self._L.nufi_b200_group_last_error(None).decode())
+
+    def step(self, n: int) -> None:
+        rc = self._L.nufi_b200_group_step(self._g, n)
+        if rc != _lib.OK:
+            _raise(rc, self._L.nufi_b200_group_last_error(self._g).decode())
+
+    def sync(self) -> None:
+        rc = self._L.nufi_b200_group_sync(self._g)
+        if rc != _lib.OK:
+            _raise(rc, self._L.nufi_b200_group_last_error(self._g).decode())
+
+    def close(self) -> None:
+        if getattr(self, "_g", None) and self._g.value:
+            self._L.nufi_b200_group_destroy(self._g)
+            self._g = C.c_void_p()
+        for s in getattr(self, "scheds", []):
+            s.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,106 @@
+"""GPU: the C++ host side.  The drop-in drivers under bin/ (the reference's bin/test_nufi_{cpu,gpu}_{1,2,3}d loops written
+against include/nufi/*.hpp over the C ABI) must reproduce the reference CPU loop's electric-energy trace (<= 1e-8), through
+the reference scheduler's five-method round trip, through the fused device-resident step, and through the CPU-shaped
+per-node eval_rho loop.  Also: the stand-alone poisson / interpolate entry points and the one-process multi-GPU group."""
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from cases import CASES, rel_linf
+from numericalflowiteration_b200 import Config1D, Config2D, Config3D, CudaGroup, CudaScheduler, F0, _lib, device_count, stride_t
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "bin", "build")
+ENERGY_TOL = 1e-8
+
+
+def landau_conf(dim, steps):
+    """What `--landau --steps N` selects in bin/nufi_drivers.hpp."""
+    if dim == 1:
+        return Config1D(Nt=steps), F0(0, 0.01, 0.5)
+    if dim == 2:
+        return Config2D(Nt=steps), F0(0, 0.05, 0.5)
+    L = 10 * math.pi
+    return Config3D(Nt=steps, x_max=L, y_max=L, z_max=L, u_min=-6, u_max=6, v_min=-6, v_max=6, w_min=-6, w_max=6), F0(0, 0.001, 0.2)
+
+
+def run_driver(name, args, tmp_path):
+    exe = os.path.join(BIN, name)
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "bin")], check=True)
+    efile = tmp_path / "energy.txt"
+    r = subprocess.run([exe, "--quiet", "--energy", str(efile)] + args, capture_output=True, text=True, cwd=tmp_path, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return np.loadtxt(efile)[:, 1], r.stdout, tmp_path
+
+
+@pytest.mark.parametrize("dim,steps", [(1, 24), (2, 8), (3, 12)])
+@pytest.mark.parametrize("mode", ["gpu", "gpu-fused", "cpu"])
+def test_driver_energy_trace(dim, steps, mode, oracle, tmp_path):
+    conf, f0 = landau_conf(dim, steps)
+    _, want, _ = oracle.run(conf, f0, steps)
+    name = f"test_nufi_{'cpu' if mode == 'cpu' else 'gpu'}_{dim}d"
+    args = ["--landau", "--steps", str(steps)] + (["--fused"] if mode == "gpu-fused" else [])
+    got, out, cwd = run_driver(name, args, tmp_path)
+    n = min(len(got), steps)
+    assert n >= steps - 1
+    rel = np.max(np.abs(got[:n] - want[:n]) / np.abs(want[:n]))
+    assert rel <= ENERGY_TOL, (dim, mode, rel)
+    if mode != "cpu":
+        rows = open(cwd / "statistics.csv").read().strip().splitlines()
+        assert rows[0].startswith('"Time"; "L1-Norm"; "L2-Norm"; "Electric Energy"')  # bin/test_nufi_gpu_2d.cpp:119-121
+        first = [float(x) for x in rows[1].split(";")]
+        assert abs(first[1] - conf_volume(conf)) <= 1e-3 * conf_volume(conf) or dim == 3  # L1 norm = int f = box volume (1d, 2d weights)
+
+
+def conf_volume(conf):
+    v = conf.Lx
+    if conf.dim >= 2:
+        v *= conf.Ly
+    return v
+
+
+@pytest.mark.parametrize("name", ["1d-landau", "2d-landau", "3d-landau"])
+def test_standalone_poisson_and_interpolate(name, oracle):
+    """poisson<double>::solve and interpolate<double,4> as separate entry points (the reference loop calls them one after
+    the other on the host, bin/test_nufi_gpu_3d.cpp:160-161)."""
+    import ctypes as C
+
+    mk, f0 = CASES[name]
+    conf = mk()
+    coeffs, _, _ = oracle.run(conf, f0, 4)
+    rho = oracle.rho(conf, f0, 3, coeffs)
+    phi_want, e_want = oracle.poisson(conf, rho)
+    level_want = oracle.interpolate(conf, phi_want)
+    L = _lib.load()
+    with CudaScheduler(conf, f0) as s:
+        data = rho.copy()
+        e = C.c_double(0)
+        assert L.nufi_b200_poisson_solve(s._h, data.ctypes.data_as(C.c_void_p), C.byref(e)) == 0
+        level = np.zeros(stride_t(conf))
+        assert L.nufi_b200_interpolate(s._h, data.ctypes.data_as(C.c_void_p), level.ctypes.data_as(C.c_void_p)) == 0
+    assert rel_linf(data, phi_want) <= 1e-12
+    assert abs(e.value - e_want) <= 1e-12 * abs(e_want)
+    assert rel_linf(level, level_want) <= 1e-11
+
+
+def test_group_one_process_multi_gpu(oracle):
+    """nufi_b200_group_step over every visible device == the single-device step (bitwise identical level on every device,
+    energy trace within tolerance of the reference CPU loop).  With one visible GPU the group degenerates to step()."""
+    mk, f0 = CASES["2d-landau"]
+    conf = mk()
+    _, want, _ = oracle.run(conf, f0, conf.Nt)
+    ndev = device_count()
+    with CudaGroup(conf, f0, devices=range(ndev)) as g:
+        for n in range(conf.Nt):
+            g.step(n)
+        g.sync()
+        energies = [s.download_energy(0, conf.Nt) for s in g.scheds]
+        levels = [s.download_phi(conf.Nt - 1) for s in g.scheds]
+    for e, lv in zip(energies, levels):
+        assert np.max(np.abs(e - want) / np.abs(want)) <= ENERGY_TOL
+        assert np.array_equal(lv, levels[0])

@@ -148,3 +148,39 @@ def test_sharded_rho_world_size_2_gloo(tmp_path):
                         "127.0.0.1", "--master-port", "29517", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "rank 0/2" in r.stdout and "rank 1/2" in r.stdout
+
+
+def test_cpp_drivers_build_and_fail_loudly_without_gpu():
+    """The C++ host side (include/nufi/*.hpp + bin/*.cpp) compiles with plain g++ against the C ABI; without a GPU the
+    drivers exit non-zero with the CUDA error (no silent CPU path)."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "bin")], check=True)
+    for name in ("test_nufi_gpu_1d", "test_nufi_gpu_2d", "test_nufi_gpu_3d", "test_nufi_cpu_1d", "test_nufi_cpu_2d", "test_nufi_cpu_3d"):
+        assert os.path.exists(os.path.join(ROOT, "bin", "build", name))
+    if _has_gpu():
+        return
+    for name in ("test_nufi_gpu_3d", "test_nufi_cpu_2d"):
+        r = subprocess.run([os.path.join(ROOT, "bin", "build", name), "--steps", "1"], capture_output=True, text=True, timeout=120)
+        assert r.returncode != 0
+        assert "error:" in r.stderr and ("CUDA" in r.stderr or "cuda" in r.stderr)
+
+
+def test_reference_layout_header_compiles_as_cxx():
+    """config_t<double> of include/nufi/config.hpp is layout-identical to the C structs (static_assert in
+    cuda_scheduler.hpp) and keeps the reference's defaults."""
+    src = r'''
+#include <nufi/cuda_scheduler.hpp>
+#include <cstdio>
+int main(){
+  nufi::dim1::config_t<double> a; nufi::dim2::config_t<double> b; nufi::dim3::config_t<double> c;
+  std::printf("%zu %zu %zu %zu %zu %zu %.17g %.17g %.17g\n", a.Nx, a.Nu, a.Nt, b.Nt, c.Nt, sizeof(c), a.dx, b.dv, c.x_max);
+  return 0; }'''
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.cpp"), "w").write(src)
+        subprocess.run(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.cpp"),
+                        "-L", os.path.dirname(_lib.LIB_PATH), "-lnufi_b200", "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH)], check=True)
+        out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()
+    c1, c2, c3 = Config1D(), Config2D(), Config3D()
+    assert [int(x) for x in out[:6]] == [256, 512, 1600, 800, 50, 35 * 8]
+    assert float(out[6]) == c1.dx and float(out[7]) == c2.dv and float(out[8]) == c3.x_max
