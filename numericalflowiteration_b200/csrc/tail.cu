@@ -224,16 +224,23 @@ struct SmallTailParams
     double *level, *raw1d, *energy_out;
 };
 
-// one separable pass along a dimension of length Nd (stride `stride`):  B[o] = sum_j A[base + j*stride] * w^(+-j*k)
+// one separable pass along a dimension of length Nd (stride `stride`):  B[o] = sum_j A[base + j*stride] * w^(+-j*k).
+// When the block has S = blockDim/N >= 2 threads per output the j-range is cut into S parts whose partial sums are
+// combined in a fixed order through `part` (S*N entries); two accumulator pairs break the FMA dependency chain.
 template <int SIGN>
-__device__ __forceinline__ void dft_pass(const double2 *A, double2 *B, int N, int Nd, int stride, const double2 *tw)
+__device__ __forceinline__ void dft_pass(const double2 *A, double2 *B, double2 *part, int N, int Nd, int stride, const double2 *tw)
 {
-    for (int o = threadIdx.x; o < N; o += blockDim.x) {
+    int S = 1;
+    while (2 * S * N <= static_cast<int>(blockDim.x) && 2 * S <= 8 && Nd % (2 * S) == 0) S *= 2;
+    const int len = Nd / S;
+    for (int t = threadIdx.x; t < S * N; t += blockDim.x) {
+        const int o = t % N, p = t / N;
         const int k = (o / stride) % Nd;
         const int base = o - k * stride;
-        double sr = 0, si = 0;
-        int idx = 0;
-        for (int j = 0; j < Nd; ++j) {
+        const int j0 = p * len;
+        int idx = static_cast<int>((static_cast<long long>(j0) * k) % Nd);
+        double sr0 = 0, si0 = 0, sr1 = 0, si1 = 0;
+        auto term = [&](int j, double &sr, double &si) {
             const double2 a = A[base + j * stride];
             const double2 w = tw[idx];
             if (SIGN < 0) { // a * (c - i s)
@@ -245,8 +252,25 @@ __device__ __forceinline__ void dft_pass(const double2 *A, double2 *B, int N, in
             }
             idx += k;
             if (idx >= Nd) idx -= Nd;
+        };
+        int j = j0;
+#pragma unroll 2
+        for (; j + 1 < j0 + len; j += 2) {
+            term(j, sr0, si0);
+            term(j + 1, sr1, si1);
         }
-        B[o] = make_double2(sr, si);
+        if (j < j0 + len) term(j, sr0, si0);
+        const double2 r = make_double2(sr0 + sr1, si0 + si1);
+        if (S == 1) B[o] = r;
+        else part[p * N + o] = r;
+    }
+    if (S > 1) {
+        __syncthreads();
+        for (int o = threadIdx.x; o < N; o += blockDim.x) {
+            double2 r = part[o];
+            for (int p = 1; p < S; ++p) { r.x += part[p * N + o].x; r.y += part[p * N + o].y; }
+            B[o] = r;
+        }
     }
 }
 
@@ -260,6 +284,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
     double2 *A = reinterpret_cast<double2 *>(sm_raw);
     double2 *B = A + N;
     double2 *twx = B + N, *twy = twx + Nx, *twz = twy + Ny;
+    double2 *part = twz + Nz; // kSmallThreads entries
 
     // ---- rho (either given, or the fixed-order sum of the backtrace kernel's per-(CTA, tile) slots)
     for (int l = threadIdx.x; l < N; l += blockDim.x) {
@@ -298,16 +323,16 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
     __syncthreads();
 
     // ---- forward transform, dimension by dimension
-    dft_pass<-1>(A, B, N, Nx, 1, twx);
+    dft_pass<-1>(A, B, part, N, Nx, 1, twx);
     __syncthreads();
     double2 *cur = B, *oth = A;
     if (T.dim >= 2) {
-        dft_pass<-1>(cur, oth, N, Ny, Nx, twy);
+        dft_pass<-1>(cur, oth, part, N, Ny, Nx, twy);
         __syncthreads();
         double2 *t = cur; cur = oth; oth = t;
     }
     if (T.dim >= 3) {
-        dft_pass<-1>(cur, oth, N, Nz, Nx * Ny, twz);
+        dft_pass<-1>(cur, oth, part, N, Nz, Nx * Ny, twz);
         __syncthreads();
         double2 *t = cur; cur = oth; oth = t;
     }
@@ -344,16 +369,16 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
     }
 
     // ---- inverse transform
-    dft_pass<1>(cur, oth, N, Nx, 1, twx);
+    dft_pass<1>(cur, oth, part, N, Nx, 1, twx);
     __syncthreads();
     { double2 *t = cur; cur = oth; oth = t; }
     if (T.dim >= 2) {
-        dft_pass<1>(cur, oth, N, Ny, Nx, twy);
+        dft_pass<1>(cur, oth, part, N, Ny, Nx, twy);
         __syncthreads();
         double2 *t = cur; cur = oth; oth = t;
     }
     if (T.dim >= 3) {
-        dft_pass<1>(cur, oth, N, Nz, Nx * Ny, twz);
+        dft_pass<1>(cur, oth, part, N, Nz, Nx * Ny, twz);
         __syncthreads();
         double2 *t = cur; cur = oth; oth = t;
     }
@@ -536,13 +561,10 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full)
             S.F = h->fin;
             h->fin_pending = false;
         }
-        const size_t smem = (2 * h->n_nodes + c.Nx + c.Ny + c.Nz) * sizeof(double2);
+        const size_t smem = (2 * h->n_nodes + c.Nx + c.Ny + c.Nz + kSmallThreads) * sizeof(double2);
         if (smem > 48 * 1024)
             NUFI_CUDA_CHECK(h, cudaFuncSetAttribute(tail_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        unsigned threads = static_cast<unsigned>((h->n_nodes + 31) / 32 * 32);
-        if (threads > kSmallThreads) threads = kSmallThreads;
-        if (threads < 128) threads = 128;
-        tail_small_kernel<<<1, threads, smem, h->stream>>>(S);
+        tail_small_kernel<<<1, kSmallThreads, smem, h->stream>>>(S);
         NUFI_CUDA_CHECK(h, cudaGetLastError());
         h->launches += 1;
         h->last_tail = "fused-1cta";
