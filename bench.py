@@ -150,7 +150,7 @@ def reference_sweep_timer(conf, f0, n, coeffs, budget_s: float):
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     from oracle.oracle_py import synthetic_history
 
     conf, f0, depth, desc = make_workload(args.workload, args.gpus)
@@ -173,7 +173,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "point-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -410,11 +410,32 @@ def run_gpu_arm(args):
                 extras.append({"workload": name, "error": repr(e)})
         line["other_workloads"] = extras
 
-    if rank == 0:
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return line if rank == 0 else None
+
+
+class _StdoutToStderr:
+    """Everything written to fd 1 while active goes to stderr (NCCL prints its version banner on stdout); the single JSON
+    line is written to the real stdout afterwards."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+def emit(line):
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 def main():
@@ -430,10 +451,9 @@ def main():
     ap.add_argument("--no-extras", dest="extras", action="store_false")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_gpu_arm(args)
+    with _StdoutToStderr():
+        line = run_reference_arm(args) if args.impl == "reference" else run_gpu_arm(args)
+    emit(line)
 
 
 if __name__ == "__main__":

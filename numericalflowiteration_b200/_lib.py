@@ -7,7 +7,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libnufi_b200.so")
+LIB_PATH = os.environ.get("NUFI_B200_LIB") or os.path.join(HERE, "lib", "libnufi_b200.so")  # override: tuning experiments only
 
 OK, ERR_RANGE, ERR_CUDA, ERR_ALLOC, ERR_ARG = 0, 1, 2, 3, 4
 

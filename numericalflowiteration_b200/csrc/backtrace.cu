@@ -208,18 +208,97 @@ __device__ __forceinline__ void step3d(Point<3> &p, const double *lev, const BtP
     p.vel[2] = fma(h * P.gz, Sz, p.vel[2]);
 }
 
-template <int DIM, int KIND, bool STAGED, bool POW2>
+// ---- "xpp" level format (tail.cu: row_poly): per (row, cell) the cubic A(tau_x) = sum_a c_a 6 N_a, stored as two
+// double2 halves [a0 a1] and [a2 a3] (row stride P.sx double2, the second half Nx further).  The x-contraction of a
+// window row becomes two Horner evaluations (value: 3 FMA, derivative A' = a1 + 2 tau (a2 + 1.5 tau a3): 2 FMA) instead of
+// eight FMAs plus the x basis; loads are 2 x 128-bit per row, conflict-free for consecutive cells.  P.gx carries the 1/3
+// of A' = 3 sum_a c_a 2 N'_a.
+template <bool STAGED> __device__ __forceinline__ double2 ld2(const double2 *p)
+{
+    if constexpr (STAGED) return *p;
+    else return __ldg(p);
+}
+
+template <int KIND, bool STAGED, bool POW2>
+__device__ __forceinline__ void step2d_xpp(Point<2> &p, const double *lev, const BtParams &P, unsigned &bad)
+{
+    if constexpr (KIND != FIRST) {
+        relocate<POW2>(p.tau[0], p.cell[0], fma(P.ncx, p.vel[0], p.tau[0]), P.Nx, bad);
+        relocate<POW2>(p.tau[1], p.cell[1], fma(P.ncy, p.vel[1], p.tau[1]), P.Ny, bad);
+    }
+    double Ny[4], Dy[4];
+    basis4(p.tau[1], Ny, Dy);
+    const double tx = p.tau[0], ta = 1.5 * tx, tb = 2.0 * tx;
+    const double2 *row = reinterpret_cast<const double2 *>(lev) + (p.cell[1] * P.sx + p.cell[0]);
+    double Sx = 0, Sy = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const double2 q01 = ld2<STAGED>(row), q23 = ld2<STAGED>(row + P.Nx);
+        const double qv = fma(tb, fma(ta, q23.y, q23.x), q01.y);
+        const double pv = fma(tx, fma(tx, fma(tx, q23.y, q23.x), q01.y), q01.x);
+        if (b == 0) { Sx = Ny[0] * qv; Sy = Dy[0] * pv; }
+        else { Sx = fma(Ny[b], qv, Sx); Sy = fma(Dy[b], pv, Sy); }
+        row += P.sx;
+    }
+    const double h = KIND == FULL ? 1.0 : 0.5;
+    p.vel[0] = fma(h * P.gx, Sx, p.vel[0]);
+    p.vel[1] = fma(h * P.gy, Sy, p.vel[1]);
+}
+
+template <int KIND, bool STAGED, bool POW2>
+__device__ __forceinline__ void step3d_xpp(Point<3> &p, const double *lev, const BtParams &P, unsigned &bad)
+{
+    if constexpr (KIND != FIRST) {
+        relocate<POW2>(p.tau[0], p.cell[0], fma(P.ncx, p.vel[0], p.tau[0]), P.Nx, bad);
+        relocate<POW2>(p.tau[1], p.cell[1], fma(P.ncy, p.vel[1], p.tau[1]), P.Ny, bad);
+        relocate<POW2>(p.tau[2], p.cell[2], fma(P.ncz, p.vel[2], p.tau[2]), P.Nz, bad);
+    }
+    double Ny[4], Dy[4], Nz[4], Dz[4];
+    basis4(p.tau[1], Ny, Dy);
+    basis4(p.tau[2], Nz, Dz);
+    const double tx = p.tau[0], ta = 1.5 * tx, tb = 2.0 * tx;
+    const double2 *plane = reinterpret_cast<const double2 *>(lev) + (p.cell[2] * P.sxy + p.cell[1] * P.sx + p.cell[0]);
+    double Sx = 0, Sy = 0, Sz = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const double2 *row = plane;
+        double r = 0, s = 0, w = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const double2 q01 = ld2<STAGED>(row), q23 = ld2<STAGED>(row + P.Nx);
+            const double qv = fma(tb, fma(ta, q23.y, q23.x), q01.y);
+            const double pv = fma(tx, fma(tx, fma(tx, q23.y, q23.x), q01.y), q01.x);
+            if (b == 0) { r = Ny[0] * qv; s = Dy[0] * pv; w = Ny[0] * pv; }
+            else { r = fma(Ny[b], qv, r); s = fma(Dy[b], pv, s); w = fma(Ny[b], pv, w); }
+            row += P.sx;
+        }
+        if (c == 0) { Sx = Nz[0] * r; Sy = Nz[0] * s; Sz = Dz[0] * w; }
+        else { Sx = fma(Nz[c], r, Sx); Sy = fma(Nz[c], s, Sy); Sz = fma(Dz[c], w, Sz); }
+        plane += P.sxy;
+    }
+    const double h = KIND == FULL ? 1.0 : 0.5;
+    p.vel[0] = fma(h * P.gx, Sx, p.vel[0]);
+    p.vel[1] = fma(h * P.gy, Sy, p.vel[1]);
+    p.vel[2] = fma(h * P.gz, Sz, p.vel[2]);
+}
+
+template <int DIM, int KIND, bool STAGED, bool POW2, bool XPP>
 __device__ __forceinline__ void step(Point<DIM> &p, const double *lev, const BtParams &P, unsigned &bad)
 {
     if constexpr (DIM == 1) step1d<KIND, STAGED, POW2>(p, lev, P, bad);
-    else if constexpr (DIM == 2) step2d<KIND, STAGED, POW2>(p, lev, P, bad);
-    else step3d<KIND, STAGED, POW2>(p, lev, P, bad);
+    else if constexpr (DIM == 2) {
+        if constexpr (XPP) step2d_xpp<KIND, STAGED, POW2>(p, lev, P, bad);
+        else step2d<KIND, STAGED, POW2>(p, lev, P, bad);
+    } else {
+        if constexpr (XPP) step3d_xpp<KIND, STAGED, POW2>(p, lev, P, bad);
+        else step3d<KIND, STAGED, POW2>(p, lev, P, bad);
+    }
 }
 
 // Robust (slow) trace of one point straight from the global history: used only for points whose fast trace
 // flagged a multi-period jump (wrap_cell).  Same arithmetic, cell index reduced with a true modulo; a full
 // kick is applied as two half kicks from the same position.
-template <int DIM> __device__ __noinline__ void slow_trace(Point<DIM> &p, const BtParams &P)
+template <int DIM, bool XPP> __device__ __noinline__ void slow_trace(Point<DIM> &p, const BtParams &P)
 {
     const int Ns[3] = {P.Nx, P.Ny, P.Nz};
     const double nc[3] = {P.ncx, P.ncy, P.ncz};
@@ -239,8 +318,8 @@ template <int DIM> __device__ __noinline__ void slow_trace(Point<DIM> &p, const 
             }
         }
         unsigned bad = 0;
-        step<DIM, FIRST, false, false>(p, lev, P, bad);
-        if (!(first || m == 0)) step<DIM, FIRST, false, false>(p, lev, P, bad);
+        step<DIM, FIRST, false, false, XPP>(p, lev, P, bad);
+        if (!(first || m == 0)) step<DIM, FIRST, false, false, XPP>(p, lev, P, bad);
     }
 }
 
@@ -289,15 +368,22 @@ constexpr unsigned kBarBytes = 2 * kMaxStages * 8; // full[8], empty[8]
 constexpr unsigned kRedBytes = 32 * 32 * 8;        // consumer-warp reduction scratch [32 warps][32 lanes]
 constexpr unsigned kSmemFixed = kBarBytes + kRedBytes;
 
-template <int DIM, int ILP> struct Tune
+#ifndef NUFI_3D_MT
+#define NUFI_3D_MT 512 // thread bound of the 3d B-spline kernel, one point per thread (128 registers)
+#endif
+#ifndef NUFI_3D_XPP_MT
+#define NUFI_3D_XPP_MT 640
+#endif
+template <int DIM, int ILP, bool XPP> struct Tune
 {
-    // thread-count upper bound handed to __launch_bounds__ (sets the register budget)
-    static constexpr int max_threads = DIM == 1 ? 1024 : (DIM == 2 ? (ILP == 1 ? 768 : 512) : (ILP == 1 ? 512 : 256));
+    // thread-count upper bound handed to __launch_bounds__ (sets the register budget); the xpp steps need fewer registers
+    static constexpr int max_threads =
+        DIM == 1 ? 1024 : (DIM == 2 ? (ILP == 1 ? 768 : 512) : (ILP == 1 ? (XPP ? NUFI_3D_XPP_MT : NUFI_3D_MT) : 256));
 };
 
 // ---------------------------------------------------------------- the kernel
-template <int DIM, int ILP, bool STAGED, bool POW2>
-__global__ void __launch_bounds__(Tune<DIM, ILP>::max_threads, 1) backtrace_kernel(const __grid_constant__ BtParams P)
+template <int DIM, int ILP, bool STAGED, bool POW2, bool XPP>
+__global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1) backtrace_kernel(const __grid_constant__ BtParams P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);
@@ -447,7 +533,7 @@ __global__ void __launch_bounds__(Tune<DIM, ILP>::max_threads, 1) backtrace_kern
             const double *lev = base + static_cast<size_t>(j) * level_doubles;
             if (P.metrics && c == c_hi) { // eval_f: half kick on level n at the starting position
 #pragma unroll
-                for (int i = 0; i < ILP; ++i) step<DIM, FIRST, STAGED, POW2>(pt[i], lev, P, bad[i]);
+                for (int i = 0; i < ILP; ++i) step<DIM, FIRST, STAGED, POW2, XPP>(pt[i], lev, P, bad[i]);
                 --j;
                 lev -= level_doubles;
             }
@@ -455,12 +541,12 @@ __global__ void __launch_bounds__(Tune<DIM, ILP>::max_threads, 1) backtrace_kern
 #pragma unroll 2
             for (; j >= j_lo; --j) {
 #pragma unroll
-                for (int i = 0; i < ILP; ++i) step<DIM, FULL, STAGED, POW2>(pt[i], lev, P, bad[i]);
+                for (int i = 0; i < ILP; ++i) step<DIM, FULL, STAGED, POW2, XPP>(pt[i], lev, P, bad[i]);
                 lev -= level_doubles;
             }
             if (c == 0 && j == 0) { // level 0: drift + half kick
 #pragma unroll
-                for (int i = 0; i < ILP; ++i) step<DIM, LAST, STAGED, POW2>(pt[i], base, P, bad[i]);
+                for (int i = 0; i < ILP; ++i) step<DIM, LAST, STAGED, POW2, XPP>(pt[i], base, P, bad[i]);
             }
             if constexpr (STAGED) {
                 __syncwarp();
@@ -477,7 +563,7 @@ __global__ void __launch_bounds__(Tune<DIM, ILP>::max_threads, 1) backtrace_kern
                 pt[i].cell[0] = ix;
                 if constexpr (DIM >= 2) pt[i].cell[1] = iy;
                 if constexpr (DIM >= 3) pt[i].cell[2] = iz;
-                slow_trace<DIM>(pt[i], P);
+                slow_trace<DIM, XPP>(pt[i], P);
             }
             // foot of the characteristic in physical coordinates (periodic image inside the box)
             const double x = P.x_min + (pt[i].cell[0] + (0.5 + pt[i].tau[0])) * P.dx;
@@ -563,10 +649,10 @@ __global__ void finish_metrics_kernel(const double *mpartials, unsigned grid, do
     }
 }
 
-template <int DIM, int ILP, bool STAGED, bool POW2>
+template <int DIM, int ILP, bool STAGED, bool POW2, bool XPP>
 cudaError_t launch_variant(const BtParams &P, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
 {
-    auto kern = backtrace_kernel<DIM, ILP, STAGED, POW2>;
+    auto kern = backtrace_kernel<DIM, ILP, STAGED, POW2, XPP>;
     if (smem_bytes > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
         if (e != cudaSuccess) return e;
@@ -575,30 +661,43 @@ cudaError_t launch_variant(const BtParams &P, unsigned grid, unsigned threads, s
     return cudaGetLastError();
 }
 
-template <int DIM, int ILP>
-cudaError_t launch_ilp(const BtParams &P, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
+template <int DIM, int ILP, bool XPP>
+cudaError_t launch_fmt(const BtParams &P, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
 {
     if (staged) {
-        return pow2 ? launch_variant<DIM, ILP, true, true>(P, grid, threads, smem_bytes, st)
-                    : launch_variant<DIM, ILP, true, false>(P, grid, threads, smem_bytes, st);
+        return pow2 ? launch_variant<DIM, ILP, true, true, XPP>(P, grid, threads, smem_bytes, st)
+                    : launch_variant<DIM, ILP, true, false, XPP>(P, grid, threads, smem_bytes, st);
     }
-    return pow2 ? launch_variant<DIM, ILP, false, true>(P, grid, threads, smem_bytes, st)
-                : launch_variant<DIM, ILP, false, false>(P, grid, threads, smem_bytes, st);
+    return pow2 ? launch_variant<DIM, ILP, false, true, XPP>(P, grid, threads, smem_bytes, st)
+                : launch_variant<DIM, ILP, false, false, XPP>(P, grid, threads, smem_bytes, st);
+}
+
+template <int DIM, int ILP>
+cudaError_t launch_ilp(const BtParams &P, bool xpp, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
+{
+    if constexpr (DIM >= 2) {
+        if (xpp) return launch_fmt<DIM, ILP, true>(P, staged, pow2, grid, threads, smem_bytes, st);
+    }
+    return launch_fmt<DIM, ILP, false>(P, staged, pow2, grid, threads, smem_bytes, st);
 }
 
 template <int DIM>
-cudaError_t launch_dim(const BtParams &P, int ilp, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes,
+cudaError_t launch_dim(const BtParams &P, int ilp, bool xpp, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes,
                        cudaStream_t st)
 {
-    return ilp == 2 ? launch_ilp<DIM, 2>(P, staged, pow2, grid, threads, smem_bytes, st)
-                    : launch_ilp<DIM, 1>(P, staged, pow2, grid, threads, smem_bytes, st);
+    return ilp == 2 ? launch_ilp<DIM, 2>(P, xpp, staged, pow2, grid, threads, smem_bytes, st)
+                    : launch_ilp<DIM, 1>(P, xpp, staged, pow2, grid, threads, smem_bytes, st);
 }
 
-int max_threads_for(int dim, int ilp)
+int max_threads_for(int dim, int ilp, bool xpp)
 {
-    if (dim == 1) return ilp == 1 ? Tune<1, 1>::max_threads : Tune<1, 2>::max_threads;
-    if (dim == 2) return ilp == 1 ? Tune<2, 1>::max_threads : Tune<2, 2>::max_threads;
-    return ilp == 1 ? Tune<3, 1>::max_threads : Tune<3, 2>::max_threads;
+    if (dim == 1) return ilp == 1 ? Tune<1, 1, false>::max_threads : Tune<1, 2, false>::max_threads;
+    if (dim == 2) {
+        if (xpp) return ilp == 1 ? Tune<2, 1, true>::max_threads : Tune<2, 2, true>::max_threads;
+        return ilp == 1 ? Tune<2, 1, false>::max_threads : Tune<2, 2, false>::max_threads;
+    }
+    if (xpp) return ilp == 1 ? Tune<3, 1, true>::max_threads : Tune<3, 2, true>::max_threads;
+    return ilp == 1 ? Tune<3, 1, false>::max_threads : Tune<3, 2, false>::max_threads;
 }
 
 bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
@@ -610,7 +709,7 @@ int env_int(const char *name, int dflt)
 }
 
 // chains (warps x points per thread) per SM beyond which a CTA-round's time grows with its width
-int saturation_chains(int dim) { return dim == 1 ? 32 : (dim == 2 ? 24 : 16); }
+int saturation_chains(int dim) { return dim == 1 ? 32 : (dim == 2 ? 40 : 24); }
 
 } // namespace
 
@@ -630,7 +729,7 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     P.metrics = metrics ? 1 : 0;
     P.ncx = -(c.dt * c.dx_inv); P.ncy = -(c.dt * c.dy_inv); P.ncz = -(c.dt * c.dz_inv);
     const double scale = h->dim == 2 ? 12.0 : 72.0;
-    P.gx = -c.dt * c.dx_inv / scale; P.gy = -c.dt * c.dy_inv / scale; P.gz = -c.dt * c.dz_inv / scale;
+    P.gx = -c.dt * c.dx_inv / scale / (h->xpp ? 3.0 : 1.0); P.gy = -c.dt * c.dy_inv / scale; P.gz = -c.dt * c.dz_inv / scale;
     P.x_min = c.x_min; P.y_min = c.y_min; P.z_min = c.z_min;
     P.dx = c.dx; P.dy = c.dy; P.dz = c.dz;
     // rho.hpp:136-137, 291-296, 441-447: du recomputed from the bounds, first node u_min + 0.5*du
@@ -688,7 +787,7 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
             if (force_ilp && ilp != force_ilp) continue;
             // 3d: one point per thread at 128 registers (16 warps) beats two points at 255 (8 warps) -- measured
             if (!force_ilp && h->dim == 3 && ilp == 2) continue;
-            const unsigned wmax = max_threads_for(h->dim, ilp) / 32 - (staged ? 1 : 0);
+            const unsigned wmax = max_threads_for(h->dim, ilp, h->xpp) / 32 - (staged ? 1 : 0);
             const unsigned long long upt = (P.Nvel + ilp - 1) / ilp;
             for (unsigned W = 1; W <= wmax; ++W) {
                 if (force_w && static_cast<int>(W) != force_w) continue;
@@ -742,15 +841,16 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     }
     NUFI_CUDA_CHECK(h, cudaEventRecord(ev_start, h->stream));
     cudaError_t e;
-    if (h->dim == 1) e = launch_dim<1>(P, ilp, staged, pow2, grid, threads, smem_bytes, h->stream);
-    else if (h->dim == 2) e = launch_dim<2>(P, ilp, staged, pow2, grid, threads, smem_bytes, h->stream);
-    else e = launch_dim<3>(P, ilp, staged, pow2, grid, threads, smem_bytes, h->stream);
+    if (h->dim == 1) e = launch_dim<1>(P, ilp, false, staged, pow2, grid, threads, smem_bytes, h->stream);
+    else if (h->dim == 2) e = launch_dim<2>(P, ilp, h->xpp, staged, pow2, grid, threads, smem_bytes, h->stream);
+    else e = launch_dim<3>(P, ilp, h->xpp, staged, pow2, grid, threads, smem_bytes, h->stream);
     NUFI_CUDA_CHECK(h, e);
     NUFI_CUDA_CHECK(h, cudaEventRecord(ev_stop, h->stream));
     h->ev_pending += 1;
     h->launches += 1;
-    if (staged) std::snprintf(h->variant_buf, sizeof(h->variant_buf), "smem-tma/ilp%d/W%u/Lc%dx%d", ilp, P.W, P.Lc, P.stages);
-    else std::snprintf(h->variant_buf, sizeof(h->variant_buf), "global/ilp%d/W%u", ilp, P.W);
+    const char *fmt = h->xpp ? "/xpp" : "";
+    if (staged) std::snprintf(h->variant_buf, sizeof(h->variant_buf), "smem-tma%s/ilp%d/W%u/Lc%dx%d", fmt, ilp, P.W, P.Lc, P.stages);
+    else std::snprintf(h->variant_buf, sizeof(h->variant_buf), "global%s/ilp%d/W%u", fmt, ilp, P.W);
     h->last_variant = h->variant_buf;
 
     if (!metrics) {

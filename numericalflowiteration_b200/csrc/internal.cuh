@@ -27,7 +27,7 @@ struct BtParams
     int first_level;                 // newest level read: n-1 (rho) or n (metrics); -1: none
     int metrics;                     // 0: eval_ftilda -> rho slots; 1: eval_f -> metric partials
     double ncx, ncy, ncz;            // -dt*dx_inv: cells per step per unit velocity, negated (drift is backwards)
-    double gx, gy, gz;               // kick factor -dt*dx_inv / (12 | 72) (2d | 3d basis scaling folded in)
+    double gx, gy, gz;               // kick factor -dt*dx_inv / (12 | 72) (2d | 3d basis scaling folded in); xpp: gx / 3
     double x_min, y_min, z_min, dx, dy, dz;
     double u0, v0, w0, du, dv, dw;   // first midpoint velocity node and spacing, computed as rho.hpp does
     double ug0, vg0, wg0, dug, dvg, dwg; // metrics: GPU-form nodes u_min + i*du + du/2 (conf.du)
@@ -71,6 +71,7 @@ struct Handle
     size_t n_nodes = 0, n_vel = 0, stride_t = 0; // reference-format level size
     // device level format
     int sx = 0, sxy = 0;
+    bool xpp = false;        // 2d/3d: levels stored as per-(row, cell) cubics in the x offset (see tail.cu: row_poly)
     size_t level_stride = 0; // doubles
     size_t raw_stride = 0;   // 1d only: raw spline level kept beside the pp-form (doubles)
     double *d_hist = nullptr, *d_raw = nullptr;

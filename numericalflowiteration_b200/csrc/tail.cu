@@ -12,6 +12,7 @@
 #include "internal.cuh"
 
 #include <cmath>
+#include <cstdio>
 
 namespace nufi_b200
 {
@@ -91,13 +92,71 @@ __device__ __forceinline__ void cell_poly_1d(const double *c, double g, double &
     p2 = g * (0.5 * ((c3 - c0) + 3.0 * (c1 - c2)));
 }
 
+// x-direction pp-form of one row-cell (2d/3d "xpp" level format): A(tau) = sum_a c_a 6 N_a(1/2 + tau)
+//   = a0 + a1 tau + a2 tau^2 + a3 tau^3  (6 N_0 = (1/2 - tau)^3, 6 N_1 = 23/8 - 15/4 tau - 3/2 tau^2 + 3 tau^3, N_2(tau) = N_1(-tau),
+//   N_3(tau) = N_0(-tau)); the x-derivative contraction sum_a c_a 2 N'_a is A'(tau)/3.
+__device__ __forceinline__ void row_poly(double c0, double c1, double c2, double c3, double2 &a01, double2 &a23)
+{
+    const double s03 = c0 + c3, s12 = c1 + c2, d30 = c3 - c0, d21 = c2 - c1;
+    a01.x = fma(2.875, s12, 0.125 * s03);
+    a01.y = fma(3.75, d21, 0.75 * d30);
+    a23.x = 1.5 * (s03 - s12);
+    a23.y = fma(-3.0, d21, d30);
+}
+
 struct ExpandParams
 {
     int dim, Nx, Ny, Nz, sx, sxy;
     size_t level_doubles; // device level size
     double g1;            // 1d: -dt*dx_inv
-    int shift;            // 0: src indexed by periodic coefficient index
+    int xpp;              // 2d/3d: level = per (row, cell) cubic in the x offset, [Q01: Nx x (a0,a1)][Q23: Nx x (a2,a3)] per row
 };
+
+// xpp level + raw reference-format level from a coefficient source.  PERIODIC: src holds Nx*Ny*Nz periodic coefficients;
+// otherwise src is a reference-format level with halo (row stride Nx+3).  One thread per (row, cell) / raw element.
+template <bool PERIODIC, typename Src>
+__device__ __forceinline__ void write_xpp(const Src &src, double *level, double *raw, const ExpandParams &E, size_t tid, size_t nthreads)
+{
+    const int rx = E.Nx + 3, ry = E.Ny + 3, rz = E.dim == 3 ? E.Nz + 3 : 1;
+    auto coef = [&](int k, int j, int i) -> double {
+        if (PERIODIC) { // every index is below 2 N (halo of 3, N >= 4): one conditional subtraction wraps it
+            const int kw = k >= E.Nz ? k - E.Nz : k, jw = j >= E.Ny ? j - E.Ny : j, iw = i >= E.Nx ? i - E.Nx : i;
+            return src((static_cast<size_t>(kw) * E.Ny + jw) * E.Nx + iw);
+        }
+        return src((static_cast<size_t>(k) * ry + j) * rx + i);
+    };
+    const size_t n_raw = static_cast<size_t>(rx) * ry * rz;
+    for (size_t idx = tid; idx < n_raw; idx += nthreads) {
+        const int i = static_cast<int>(idx % rx);
+        const size_t rest = idx / rx;
+        raw[idx] = coef(static_cast<int>(rest / ry), static_cast<int>(rest % ry), i);
+    }
+    const size_t n_cells = static_cast<size_t>(E.Nx) * ry * rz;
+    double2 *lv = reinterpret_cast<double2 *>(level);
+    for (size_t idx = tid; idx < n_cells; idx += nthreads) {
+        const int i = static_cast<int>(idx % E.Nx);
+        const size_t r = idx / E.Nx;
+        const int j = static_cast<int>(r % ry), k = static_cast<int>(r / ry);
+        double2 a01, a23;
+        row_poly(coef(k, j, i), coef(k, j, i + 1), coef(k, j, i + 2), coef(k, j, i + 3), a01, a23);
+        lv[r * 2 * E.Nx + i] = a01;
+        lv[r * 2 * E.Nx + E.Nx + i] = a23;
+    }
+}
+
+__global__ void expand_xpp_kernel(const double *src, double *level, double *raw, ExpandParams E, int periodic, const double *epart,
+                                  unsigned n_epart, double vol_half, double *energy_out)
+{
+    const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x, nth = static_cast<size_t>(gridDim.x) * blockDim.x;
+    auto get = [&](size_t i) { return src[i]; };
+    if (periodic) write_xpp<true>(get, level, raw, E, tid, nth);
+    else write_xpp<false>(get, level, raw, E, tid, nth);
+    if (energy_out && blockIdx.x == 0 && threadIdx.x == 0) {
+        double s = 0;
+        for (unsigned b = 0; b < n_epart; ++b) s += epart[b];
+        *energy_out = s * vol_half;
+    }
+}
 
 // Periodic coefficients (Nx*Ny*Nz, x fastest) -> device level with (order-1) halo
 // (the copy loops of nufi/fields.hpp:140-141, 294-299, 482-489), 2d/3d.
@@ -181,8 +240,10 @@ __global__ void ref_to_device_kernel(const double *ref, double *level, double *r
 
 __global__ void device_to_ref_kernel(const double *level, const double *raw1d, double *ref, ExpandParams E)
 {
-    if (E.dim == 1) {
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < E.Nx + 3; i += gridDim.x * blockDim.x) ref[i] = raw1d[i];
+    if (E.dim == 1 || E.xpp) { // the raw reference-format level is kept beside the pp-form
+        const size_t total = static_cast<size_t>(E.Nx + 3) * (E.dim >= 2 ? E.Ny + 3 : 1) * (E.dim >= 3 ? E.Nz + 3 : 1);
+        for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+            ref[i] = raw1d[i];
         return;
     }
     const int rx = E.Nx + 3, ry = E.Ny + 3, rz = E.dim == 3 ? E.Nz + 3 : 1;
@@ -213,6 +274,7 @@ __global__ void full_rho_kernel(const double *partial_sum, double *full, size_t 
 constexpr int kSmallMaxNodes = 4096;
 constexpr int kSmallMaxDim = 256;
 constexpr int kSmallThreads = 1024;
+constexpr int kSmallPart = 4096; // double2 scratch: DFT partial sums (<= kSmallThreads) / slot partials (8 x N doubles, N < 1024)
 
 struct SmallTailParams
 {
@@ -274,8 +336,63 @@ __device__ __forceinline__ void dft_pass(const double2 *A, double2 *B, double2 *
     }
 }
 
+// Radix-2 Stockham FFT along a power-of-two dimension, all lines of the grid at once (N/2 butterflies per stage, ping-pong
+// between the two buffers, twiddles from the exact table).  Returns with the result in `cur` (pointers swapped as needed).
+template <int SIGN>
+__device__ __forceinline__ void fft_pass(double2 *&cur, double2 *&oth, int N, int Nd, int stride, const double2 *tw)
+{
+    const int half = Nd >> 1;
+    const int lh = 31 - __clz(half); // log2(half)
+    int ls = 0;                      // log2(Ns)
+    for (int Ns = 1; Ns < Nd; Ns <<= 1, ++ls) {
+        const int tshift = lh - ls;  // twiddle index step = Nd / (2 Ns)
+        for (int t = threadIdx.x; t < (N >> 1); t += blockDim.x) {
+            int lo = 0, q = t;
+            if (stride != 1) { q = t / stride; lo = t - q * stride; }
+            const int j = q & (half - 1);
+            const int hi = q >> lh;
+            const int base = hi * stride * Nd + lo;
+            const int kk = j & (Ns - 1);
+            const double2 v0 = cur[base + j * stride];
+            const double2 u = cur[base + (j + half) * stride];
+            const double2 w = tw[kk << tshift];
+            double2 v1; // u * exp(SIGN * i * angle)
+            if (SIGN < 0) v1 = make_double2(fma(u.x, w.x, u.y * w.y), fma(u.y, w.x, -u.x * w.y));
+            else v1 = make_double2(fma(u.x, w.x, -u.y * w.y), fma(u.y, w.x, u.x * w.y));
+            const int d = ((j >> ls) << (ls + 1)) + kk;
+            oth[base + d * stride] = make_double2(v0.x + v1.x, v0.y + v1.y);
+            oth[base + (d + Ns) * stride] = make_double2(v0.x - v1.x, v0.y - v1.y);
+        }
+        __syncthreads();
+        double2 *tmp = cur; cur = oth; oth = tmp;
+    }
+}
+
+// transform along one dimension: FFT when its length is a power of two (>= 8), direct sums otherwise
+template <int SIGN>
+__device__ __forceinline__ void transform_dim(double2 *&cur, double2 *&oth, double2 *part, int N, int Nd, int stride, const double2 *tw)
+{
+    if (Nd >= 8 && (Nd & (Nd - 1)) == 0) {
+        fft_pass<SIGN>(cur, oth, N, Nd, stride, tw);
+    } else {
+        dft_pass<SIGN>(cur, oth, part, N, Nd, stride, tw);
+        __syncthreads();
+        double2 *tmp = cur; cur = oth; oth = tmp;
+    }
+}
+
+#ifdef NUFI_TAIL_TIMING
+#define TAIL_MARK(i) do { __syncthreads(); if (threadIdx.x == 0) tmark[i] = clock64(); } while (0)
+#else
+#define TAIL_MARK(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __grid_constant__ SmallTailParams S)
 {
+#ifdef NUFI_TAIL_TIMING
+    __shared__ long long tmark[8];
+#endif
+    TAIL_MARK(0);
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __shared__ double red[32];
     const TailParams &T = S.T;
@@ -284,59 +401,74 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
     double2 *A = reinterpret_cast<double2 *>(sm_raw);
     double2 *B = A + N;
     double2 *twx = B + N, *twy = twx + Nx, *twz = twy + Ny;
-    double2 *part = twz + Nz; // kSmallThreads entries
+    double2 *ilx = twz + Nz, *ily = ilx + Nx, *ilz = ily + Ny;
+    double *kap2x = reinterpret_cast<double *>(ilz + Nz), *kap2y = kap2x + Nx, *kap2z = kap2y + Ny;
+    double2 *part = reinterpret_cast<double2 *>(kap2x + ((Nx + Ny + Nz + 1) & ~1)); // kSmallPart entries
 
-    // ---- rho (either given, or the fixed-order sum of the backtrace kernel's per-(CTA, tile) slots)
-    for (int l = threadIdx.x; l < N; l += blockDim.x) {
-        double r;
-        if (S.rho) {
-            r = S.rho[l];
-        } else {
-            const FinishParams &F = S.F;
-            const unsigned tile = static_cast<unsigned>(l) >> 5, lane = l & 31;
-            const unsigned b_lo = (tile * F.rpt) / F.rpc;
-            const unsigned b_hi = ((tile + 1) * F.rpt - 1) / F.rpc;
-            // same association as finish_rho_kernel: 8 strided partial sums, then added in order
-            double part[8];
-#pragma unroll
-            for (int w = 0; w < 8; ++w) part[w] = 0;
-            for (unsigned b0 = b_lo; b0 <= b_hi; b0 += 8) {
-#pragma unroll
-                for (int w = 0; w < 8; ++w) {
-                    const unsigned b = b0 + w;
-                    if (b <= b_hi) {
-                        const unsigned t_first = (b * F.rpc) / F.rpt;
-                        part[w] += F.slots[(static_cast<size_t>(b) * F.Tmax + (tile - t_first)) * 32 + lane];
-                    }
-                }
+    // ---- tables into shared memory first (their global-memory latency overlaps the slot reduction)
+    for (int i = threadIdx.x; i < Nx + Ny + Nz; i += blockDim.x) {
+        twx[i] = S.twx[i]; // the three tables of a kind are contiguous
+        ilx[i] = T.ilx[i];
+        kap2x[i] = T.kap2x[i];
+    }
+    // ---- rho (either given, or the fixed-order sum of the backtrace kernel's per-(CTA, tile) slots: per node 8 strided
+    //      partial sums over the CTAs that touched its tile, then added in order -- the association of finish_rho_kernel)
+    if (S.rho) {
+        for (int l = threadIdx.x; l < N; l += blockDim.x) A[l] = make_double2(S.rho[l], 0.0);
+    } else {
+        const FinishParams &F = S.F;
+        auto slot_sum = [&](unsigned tile, unsigned lane, unsigned b_lo, unsigned b_hi, int w) {
+            double sum = 0;
+            for (unsigned b = b_lo + w; b <= b_hi; b += 8) {
+                const unsigned t_first = (b * F.rpc) / F.rpt;
+                sum += F.slots[(static_cast<size_t>(b) * F.Tmax + (tile - t_first)) * 32 + lane];
             }
-            double tot = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) tot += part[w];
-            r = 1 - F.dV * tot;
+            return sum;
+        };
+        auto store_rho = [&](int l, double tot) {
+            const double r = 1 - F.dV * tot;
             F.rho_partial[l] = -F.dV * tot;
             if (F.rho_full) F.rho_full[l] = r;
+            A[l] = make_double2(r, 0.0);
+        };
+        if (8 * N <= 2 * kSmallPart) { // small grids: spread the 8 partial sums of a node over up to 8 threads
+            int G = 1;                 // threads per node
+            while (2 * G * N <= static_cast<int>(blockDim.x) && G < 8) G *= 2;
+            double *ps = reinterpret_cast<double *>(part); // [8][N]
+            for (int it = threadIdx.x; it < N * G; it += blockDim.x) {
+                const int l = it % N, g = it / N;
+                const unsigned tile = static_cast<unsigned>(l) >> 5, lane = l & 31;
+                const unsigned b_lo = (tile * F.rpt) / F.rpc, b_hi = ((tile + 1) * F.rpt - 1) / F.rpc;
+                for (int w = g; w < 8; w += G) ps[w * N + l] = slot_sum(tile, lane, b_lo, b_hi, w);
+            }
+            __syncthreads();
+            for (int l = threadIdx.x; l < N; l += blockDim.x) {
+                double tot = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) tot += ps[w * N + l];
+                store_rho(l, tot);
+            }
+        } else {
+            for (int l = threadIdx.x; l < N; l += blockDim.x) {
+                const unsigned tile = static_cast<unsigned>(l) >> 5, lane = l & 31;
+                const unsigned b_lo = (tile * F.rpt) / F.rpc, b_hi = ((tile + 1) * F.rpt - 1) / F.rpc;
+                double tot = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) tot += slot_sum(tile, lane, b_lo, b_hi, w);
+                store_rho(l, tot);
+            }
         }
-        A[l] = make_double2(r, 0.0);
     }
-    for (int i = threadIdx.x; i < Nx + Ny + Nz; i += blockDim.x) twx[i] = S.twx[i]; // the three tables are contiguous
     __syncthreads();
+    TAIL_MARK(1);
 
     // ---- forward transform, dimension by dimension
-    dft_pass<-1>(A, B, part, N, Nx, 1, twx);
-    __syncthreads();
-    double2 *cur = B, *oth = A;
-    if (T.dim >= 2) {
-        dft_pass<-1>(cur, oth, part, N, Ny, Nx, twy);
-        __syncthreads();
-        double2 *t = cur; cur = oth; oth = t;
-    }
-    if (T.dim >= 3) {
-        dft_pass<-1>(cur, oth, part, N, Nz, Nx * Ny, twz);
-        __syncthreads();
-        double2 *t = cur; cur = oth; oth = t;
-    }
+    double2 *cur = A, *oth = B;
+    transform_dim<-1>(cur, oth, part, N, Nx, 1, twx);
+    if (T.dim >= 2) transform_dim<-1>(cur, oth, part, N, Ny, Nx, twy);
+    if (T.dim >= 3) transform_dim<-1>(cur, oth, part, N, Nz, Nx * Ny, twz);
 
+    TAIL_MARK(2);
     // ---- Poisson x collocation symbol, energy in Fourier space (full spectrum: every mode counted once)
     double e = 0;
     for (int idx = threadIdx.x; idx < N; idx += blockDim.x) {
@@ -349,11 +481,11 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
             continue;
         }
         const double2 Fk = cur[idx];
-        const double kap2 = T.kap2x[kx] + T.kap2y[ky] + T.kap2z[kz];
+        const double kap2 = kap2x[kx] + kap2y[ky] + kap2z[kz];
         const double fac = T.fac_N / kap2;
         const double pr = Fk.x * fac, pi = Fk.y * fac;
         e += kap2 * (pr * pr + pi * pi);
-        const double2 a = T.ilx[kx], b = T.ily[ky], c = T.ilz[kz];
+        const double2 a = ilx[kx], b = ily[ky], c = ilz[kz];
         const double2 ab = make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
         const double2 s = make_double2(ab.x * c.x - ab.y * c.y, ab.x * c.y + ab.y * c.x);
         cur[idx] = make_double2(pr * s.x - pi * s.y, pr * s.y + pi * s.x);
@@ -369,20 +501,13 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
     }
 
     // ---- inverse transform
-    dft_pass<1>(cur, oth, part, N, Nx, 1, twx);
     __syncthreads();
-    { double2 *t = cur; cur = oth; oth = t; }
-    if (T.dim >= 2) {
-        dft_pass<1>(cur, oth, part, N, Ny, Nx, twy);
-        __syncthreads();
-        double2 *t = cur; cur = oth; oth = t;
-    }
-    if (T.dim >= 3) {
-        dft_pass<1>(cur, oth, part, N, Nz, Nx * Ny, twz);
-        __syncthreads();
-        double2 *t = cur; cur = oth; oth = t;
-    }
+    TAIL_MARK(3);
+    transform_dim<1>(cur, oth, part, N, Nx, 1, twx);
+    if (T.dim >= 2) transform_dim<1>(cur, oth, part, N, Ny, Nx, twy);
+    if (T.dim >= 3) transform_dim<1>(cur, oth, part, N, Nz, Nx * Ny, twz);
 
+    TAIL_MARK(4);
     // ---- level n: periodic coefficients (real part) -> device level format
     const ExpandParams &E = S.E;
     if (E.dim == 1) {
@@ -397,6 +522,9 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
             S.level[3 * k + 2] = p2;
         }
         if (threadIdx.x == 0 && (3 * Nx) % 2) S.level[3 * Nx] = 0;
+    } else if (E.xpp) {
+        auto get = [&](size_t i) { return cur[i].x; };
+        write_xpp<true>(get, S.level, S.raw1d, E, threadIdx.x, blockDim.x);
     } else {
         const int rows = Ny + 3;
         for (size_t idx = threadIdx.x; idx < E.level_doubles; idx += blockDim.x) {
@@ -409,6 +537,12 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
             S.level[idx] = v;
         }
     }
+#ifdef NUFI_TAIL_TIMING
+    TAIL_MARK(5);
+    if (threadIdx.x == 0)
+        printf("tail phases (cycles): rho+tw %lld  fwd %lld  symbol %lld  inv %lld  expand %lld  total %lld\n", tmark[1] - tmark[0],
+               tmark[2] - tmark[1], tmark[3] - tmark[2], tmark[4] - tmark[3], tmark[5] - tmark[4], tmark[5] - tmark[0]);
+#endif
 }
 
 ExpandParams expand_params(const Handle *h)
@@ -417,6 +551,7 @@ ExpandParams expand_params(const Handle *h)
     E.dim = h->dim;
     E.Nx = static_cast<int>(h->c.Nx); E.Ny = static_cast<int>(h->c.Ny); E.Nz = static_cast<int>(h->c.Nz);
     E.sx = h->sx; E.sxy = h->sxy;
+    E.xpp = h->xpp ? 1 : 0;
     E.level_doubles = h->level_stride;
     E.g1 = -h->c.dt * h->c.dx_inv;
     return E;
@@ -551,7 +686,7 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full)
         S.T = T; S.E = E;
         S.twx = reinterpret_cast<const double2 *>(h->d_twiddle); S.twy = S.twx + c.Nx; S.twz = S.twy + c.Ny;
         S.level = level;
-        S.raw1d = h->dim == 1 ? h->d_raw + n * h->raw_stride : nullptr;
+        S.raw1d = h->d_raw ? h->d_raw + n * h->raw_stride : nullptr;
         S.energy_out = h->d_energy + n;
         if (d_rho_full) {
             S.rho = d_rho_full;
@@ -561,7 +696,7 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full)
             S.F = h->fin;
             h->fin_pending = false;
         }
-        const size_t smem = (2 * h->n_nodes + c.Nx + c.Ny + c.Nz + kSmallThreads) * sizeof(double2);
+        const size_t smem = (2 * h->n_nodes + 2 * (c.Nx + c.Ny + c.Nz) + kSmallPart) * sizeof(double2) + ((c.Nx + c.Ny + c.Nz + 1) & ~size_t(1)) * sizeof(double);
         if (smem > 48 * 1024)
             NUFI_CUDA_CHECK(h, cudaFuncSetAttribute(tail_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         tail_small_kernel<<<1, kSmallThreads, smem, h->stream>>>(S);
@@ -590,6 +725,9 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full)
     if (h->dim == 1) {
         expand1d_kernel<<<blocks_for(c.Nx + 3, 256, 64), 256, 0, h->stream>>>(h->d_field, h->d_raw + n * h->raw_stride, level, E,
                                                                           h->d_epart, sblocks, vol_half, h->d_energy + n);
+    } else if (h->xpp) {
+        expand_xpp_kernel<<<blocks_for(h->stride_t, 256, 1184), 256, 0, h->stream>>>(h->d_field, level, h->d_raw + n * h->raw_stride, E, 1,
+                                                                                     h->d_epart, sblocks, vol_half, h->d_energy + n);
     } else {
         expand_kernel<<<blocks_for(h->level_stride, 256, 1184), 256, 0, h->stream>>>(h->d_field, level, E, 0.0, h->d_epart, sblocks,
                                                                                      vol_half, h->d_energy + n);
@@ -673,6 +811,10 @@ double *tail_energy_scratch(Handle *h) { return h->d_epart + kSymbolBlocks; }
 int convert_level_to_device(Handle *h, size_t n, const double *d_ref_level)
 {
     ExpandParams E = expand_params(h);
+    if (h->xpp)
+        expand_xpp_kernel<<<blocks_for(h->stride_t, 256, 1184), 256, 0, h->stream>>>(d_ref_level, h->d_hist + n * h->level_stride,
+                                                                                     h->d_raw + n * h->raw_stride, E, 0, nullptr, 0, 0.0, nullptr);
+    else
     ref_to_device_kernel<<<blocks_for(h->level_stride, 256, 1184), 256, 0, h->stream>>>(
         d_ref_level, h->d_hist + n * h->level_stride, h->dim == 1 ? h->d_raw + n * h->raw_stride : nullptr, E);
     NUFI_CUDA_CHECK(h, cudaGetLastError());
@@ -684,7 +826,7 @@ int convert_level_from_device(Handle *h, size_t n, double *d_ref_level)
 {
     ExpandParams E = expand_params(h);
     device_to_ref_kernel<<<blocks_for(h->stride_t, 256, 1184), 256, 0, h->stream>>>(
-        h->d_hist + n * h->level_stride, h->dim == 1 ? h->d_raw + n * h->raw_stride : nullptr, d_ref_level, E);
+        h->d_hist + n * h->level_stride, h->d_raw ? h->d_raw + n * h->raw_stride : nullptr, d_ref_level, E);
     NUFI_CUDA_CHECK(h, cudaGetLastError());
     h->launches += 1;
     return NUFI_B200_OK;

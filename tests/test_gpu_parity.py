@@ -29,8 +29,14 @@ def histories(oracle):
 
 @pytest.mark.parametrize("name", list(CASES))
 @pytest.mark.parametrize("variant", [1, 2])
-def test_rho_teacher_forced(name, variant, histories, oracle):
+@pytest.mark.parametrize("xpp", [0, 1], ids=["bspline-levels", "xpp-levels"])
+def test_rho_teacher_forced(name, variant, xpp, histories, oracle, monkeypatch):
+    """variant: 1 global-memory kernel, 2 shared-memory staged kernel; xpp: level format of 2d/3d histories (B-spline
+    window vs per-row cubics in x)."""
     conf, f0, coeffs, _ = histories[name]
+    if conf.dim == 1 and xpp:
+        pytest.skip("1d has a single level format")
+    monkeypatch.setenv("NUFI_B200_XPP", str(xpp))
     with CudaScheduler(conf, f0) as s:
         s.set_variant(variant)
         s.upload_history(coeffs, conf.Nt)
@@ -90,9 +96,10 @@ def test_field_tail(name, tail, histories, oracle):
 
 @pytest.mark.parametrize("tail", [0, 1], ids=["tail-auto", "tail-cufft"])
 @pytest.mark.parametrize("name", ["1d-two-stream", "1d-landau", "2d-landau", "3d-landau", "3d-bump"])
-def test_free_run_energy_trace(name, tail, histories):
+def test_free_run_energy_trace(name, tail, histories, monkeypatch):
     """The fused step() loop, no host round trip, against the reference CPU loop."""
     conf, f0, coeffs, energy = histories[name]
+    monkeypatch.setenv("NUFI_B200_XPP", str(tail))  # tail-auto with B-spline levels, tail-cufft with xpp levels
     with CudaScheduler(conf, f0) as s:
         s.set_tail_variant(tail)
         for n in range(conf.Nt):
@@ -105,9 +112,11 @@ def test_free_run_energy_trace(name, tail, histories):
     assert rel_linf(last, coeffs[(conf.Nt - 1) * st: conf.Nt * st]) <= 1e-8
 
 
-def test_upload_download_roundtrip_and_errors(histories):
+@pytest.mark.parametrize("xpp", [0, 1])
+def test_upload_download_roundtrip_and_errors(xpp, histories, monkeypatch):
     conf, f0, coeffs, _ = histories["2d-landau"]
     st = stride_t(conf)
+    monkeypatch.setenv("NUFI_B200_XPP", str(xpp))
     with CudaScheduler(conf, f0) as s:
         s.upload_phi(2, coeffs)
         assert np.array_equal(s.download_phi(2), coeffs[2 * st:3 * st])
@@ -180,3 +189,31 @@ def test_multi_period_jump_in_one_step(nx, oracle):
         for n in (1, 3, conf.Nt):
             got = s.eval_rho(n)
             assert rel_linf(got, oracle.rho(conf, f0, n, coeffs)) <= RHO_TOL, (nx, n)
+
+
+@pytest.mark.parametrize("shape", ["1d-256", "1d-512", "2d-32x32", "2d-64x32", "3d-16^3", "3d-8x16x4"])
+def test_fused_step_grid_sizes(shape, oracle):
+    """The fused step (slot reduction + field tail in one CTA, or the cuFFT tail above 4096 nodes / 256 per dimension) on
+    the grid sizes of the benchmark configurations; few velocities so the CPU oracle stays cheap."""
+    import math
+
+    L = 10 * math.pi
+    if shape.startswith("1d"):
+        conf, f0 = conf1d(Nx=int(shape[3:]), Nu=32, Nt=6), F0(1, 0.01, 0.5)
+    elif shape.startswith("2d"):
+        nx, ny = (int(v) for v in shape[3:].split("x"))
+        conf, f0 = conf2d(Nx=nx, Ny=ny, Nu=6, Nv=4, Nt=5), F0(0, 0.05, 0.5)
+    else:
+        dims = (16, 16, 16) if shape == "3d-16^3" else (8, 16, 4)
+        conf, f0 = conf3d(Nx=dims[0], Ny=dims[1], Nz=dims[2], Nu=3, Nv=2, Nw=2, Nt=4), F0(0, 0.001, 0.2)
+    coeffs, energy, _ = oracle.run(conf, f0, conf.Nt)
+    with CudaScheduler(conf, f0) as s:
+        for n in range(conf.Nt):
+            s.step(n)
+        got = s.download_energy(0, conf.Nt)
+        last = s.download_phi(conf.Nt - 1)
+        rho = s.eval_rho(conf.Nt)
+    assert np.max(np.abs(got - energy) / np.abs(energy)) <= ENERGY_TOL, (shape, s.last_tail_variant)
+    st = stride_t(conf)
+    assert rel_linf(last, coeffs[(conf.Nt - 1) * st: conf.Nt * st]) <= 1e-8
+    assert rel_linf(rho, oracle.rho(conf, f0, conf.Nt, coeffs)) <= 1e-9  # own (free-running) history vs oracle history

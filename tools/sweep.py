@@ -24,9 +24,12 @@ def main():
     ap.add_argument("--W", type=int, nargs="*", default=[0])
     ap.add_argument("--lc", type=int, nargs="*", default=[0])
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--xpp", type=int, default=-1, help="level format of 2d/3d histories: 0 B-spline, 1 xpp, -1 auto")
     a = ap.parse_args()
     conf, f0, depth, desc = make_workload(a.workload, 1)
     n = a.depth or depth
+    if a.xpp >= 0:
+        os.environ["NUFI_B200_XPP"] = str(a.xpp)
     torch.cuda.set_device(0)
     r = GpuRunner(conf, f0, 0, 1, torch, None)
     free_run(r, n)
