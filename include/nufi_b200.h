@@ -146,6 +146,21 @@ int nufi_b200_download_energy(nufi_b200_handle *h, size_t n_begin, size_t n_end,
 int nufi_b200_download_phi(nufi_b200_handle *h, size_t n, double *coeffs_level);
 int nufi_b200_sync(nufi_b200_handle *h);
 
+/* ---- checkpoint / restart: the coefficient history IS the complete state.  Levels 0..n_levels-1 in the
+ *      reference layout, n_levels*stride_t doubles -- what bin/test_nufi_gpu_1d.cpp:239,364-366 and
+ *      bin/test_nufi_cpu_3d_isolated.cpp:64-73,160-163 write as text (readers/writers: include/nufi/history_io.hpp).
+ *      Restart = upload_history + continue stepping at n_levels: bit-identical to the uninterrupted run.  Blocking. ---- */
+int nufi_b200_download_history(nufi_b200_handle *h, size_t n_levels, double *coeffs_host);
+int nufi_b200_upload_history(nufi_b200_handle *h, size_t n_levels, const double *coeffs_host);
+
+/* ---- sampling for plots / diagnostics (bin/test_nufi_gpu_1d.cpp:307-349, bin/test_nufi_gpu_2d.cpp:174-200), host buffers,
+ *      blocking.  eval_f: f(t_n, x, v) at npts phase-space points, points = [npts][2*dim] (x.., v..); with_first_half_kick
+ *      1 = eval_f (needs levels 0..n; nufi/rho.hpp:63-96, 234-281, 369-426), 0 = eval_ftilda (levels 0..n-1).
+ *      eval_field: phi_n (derivative_axis = -1) or d phi_n / d x_axis at npts positions, points = [npts][dim]
+ *      (nufi/fields.hpp:36-61, 149-184, 308-350). ---- */
+int nufi_b200_eval_f(nufi_b200_handle *h, size_t n, size_t npts, const double *points_host, double *f_host, int with_first_half_kick);
+int nufi_b200_eval_field(nufi_b200_handle *h, size_t n, int derivative_axis, size_t npts, const double *points_host, double *values_host);
+
 /* ---- device-pointer plumbing for one-process-per-GPU callers (torch.distributed / NCCL host layer) ---- */
 /* run all work of h on this cudaStream_t (NULL = the handle's own stream) */
 int nufi_b200_set_stream(nufi_b200_handle *h, void *cuda_stream);

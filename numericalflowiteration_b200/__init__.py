@@ -9,8 +9,9 @@ reference's ``config_t`` / ``cuda_scheduler`` interface.  There is no CPU fallba
 from .config import Config1D, Config2D, Config3D, F0, n_nodes, n_quad, n_vel, stride_t
 from .scheduler import CudaError, CudaGroup, CudaScheduler, RangeError, device_count, measure_fp64_peak
 from .distributed import partition, DistributedStepper
+from . import history_io
 
 __all__ = [
     "Config1D", "Config2D", "Config3D", "F0", "n_nodes", "n_quad", "n_vel", "stride_t",
-    "CudaScheduler", "CudaGroup", "device_count", "CudaError", "RangeError", "measure_fp64_peak", "partition", "DistributedStepper",
+    "CudaScheduler", "CudaGroup", "device_count", "CudaError", "RangeError", "measure_fp64_peak", "partition", "DistributedStepper", "history_io",
 ]

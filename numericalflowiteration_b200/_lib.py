@@ -17,7 +17,8 @@ SYMBOLS = [
     "nufi_b200_compute_rho", "nufi_b200_download_rho", "nufi_b200_upload_phi", "nufi_b200_compute_metrics",
     "nufi_b200_download_metrics", "nufi_b200_eval_rho_all", "nufi_b200_solve_interpolate",
     "nufi_b200_solve_interpolate_host", "nufi_b200_poisson_solve", "nufi_b200_interpolate", "nufi_b200_step", "nufi_b200_download_energy", "nufi_b200_download_phi",
-    "nufi_b200_sync", "nufi_b200_set_stream", "nufi_b200_rho_device", "nufi_b200_field_tail_device",
+    "nufi_b200_sync", "nufi_b200_download_history", "nufi_b200_upload_history", "nufi_b200_eval_f",
+    "nufi_b200_eval_field", "nufi_b200_set_stream", "nufi_b200_rho_device", "nufi_b200_field_tail_device",
     "nufi_b200_launch_count", "nufi_b200_last_backtrace_ms", "nufi_b200_backtrace_time", "nufi_b200_last_variant", "nufi_b200_set_variant",
     "nufi_b200_set_tail_variant", "nufi_b200_last_tail_variant", "nufi_b200_measure_fp64_peak", "nufi_b200_version",
     "nufi_b200_group_create", "nufi_b200_group_destroy", "nufi_b200_group_step", "nufi_b200_group_sync",
@@ -60,6 +61,8 @@ def load() -> C.CDLL:
         "rho_device": [vp, C.POINTER(vp)], "field_tail_device": [vp, sz, vp], "last_backtrace_ms": [vp, C.POINTER(C.c_float)],
         "set_variant": [vp, i], "measure_fp64_peak": [i, dp],
         "backtrace_time": [vp, dp, C.POINTER(C.c_uint64), i], "set_tail_variant": [vp, i],
+        "download_history": [vp, sz, vp], "upload_history": [vp, sz, vp], "eval_f": [vp, sz, sz, vp, vp, i],
+        "eval_field": [vp, sz, i, sz, vp, vp],
         "poisson_solve": [vp, vp, dp], "interpolate": [vp, vp, vp], "device_count": [C.POINTER(i)], "device_of": [vp],
         "group_create": [C.POINTER(vp), i, C.POINTER(vp)], "group_step": [vp, sz], "group_sync": [vp],
     }.items():

@@ -421,6 +421,82 @@ int nufi_b200_download_phi(nufi_b200_handle *h, size_t n, double *coeffs_level)
     return NUFI_B200_OK;
 }
 
+// ---- bulk history transfer (checkpoint / restart): the coefficient history is the complete simulation state
+int nufi_b200_download_history(nufi_b200_handle *h, size_t n_levels, double *coeffs_host)
+{
+    ENTER(h);
+    if (n_levels > hh->Nt + 1) return fail(hh, NUFI_B200_ERR_RANGE, "more levels requested than the history holds");
+    if (n_levels && !coeffs_host) return fail(hh, NUFI_B200_ERR_ARG, "coeffs is NULL");
+    int rc = check_levels(hh, n_levels, "download_history");
+    if (rc) return rc;
+    for (size_t m = 0; m < n_levels; ++m) {
+        rc = nufi_b200_download_phi(h, m, coeffs_host + m * hh->stride_t);
+        if (rc) return rc;
+    }
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_upload_history(nufi_b200_handle *h, size_t n_levels, const double *coeffs_host)
+{
+    ENTER(h);
+    if (n_levels > hh->Nt + 1) return fail(hh, NUFI_B200_ERR_RANGE, "more levels than the history can hold");
+    if (n_levels && !coeffs_host) return fail(hh, NUFI_B200_ERR_ARG, "coeffs is NULL");
+    for (size_t m = 0; m < n_levels; ++m) {
+        int rc = nufi_b200_upload_phi(h, m, coeffs_host);
+        if (rc) return rc;
+    }
+    return NUFI_B200_OK;
+}
+
+// ---- sampling for plots / diagnostics (host buffers, blocking)
+namespace
+{
+struct DeviceScratch
+{
+    double *p = nullptr;
+    ~DeviceScratch() { cudaFree(p); }
+};
+} // namespace
+
+int nufi_b200_eval_f(nufi_b200_handle *h, size_t n, size_t npts, const double *points_host, double *f_host, int with_first_half_kick)
+{
+    ENTER(h);
+    if (n > hh->Nt) return fail(hh, NUFI_B200_ERR_RANGE, "Time-step out of range.");
+    if (npts == 0) return NUFI_B200_OK;
+    if (!points_host || !f_host) return fail(hh, NUFI_B200_ERR_ARG, "points / f is NULL");
+    int rc = check_levels(hh, with_first_half_kick ? (n == 0 ? 0 : n + 1) : n, "eval_f");
+    if (rc) return rc;
+    const size_t w = 2 * static_cast<size_t>(hh->dim);
+    DeviceScratch d;
+    if (cudaMalloc(&d.p, sizeof(double) * npts * (w + 1)) != cudaSuccess) return fail(hh, NUFI_B200_ERR_ALLOC, "cudaMalloc of the sample points failed");
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(d.p, points_host, sizeof(double) * npts * w, cudaMemcpyHostToDevice, hh->stream));
+    rc = launch_sample_f(hh, n, npts, d.p, d.p + npts * w, with_first_half_kick != 0);
+    if (rc) return rc;
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(f_host, d.p + npts * w, sizeof(double) * npts, cudaMemcpyDeviceToHost, hh->stream));
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_eval_field(nufi_b200_handle *h, size_t n, int derivative_axis, size_t npts, const double *points_host, double *values_host)
+{
+    ENTER(h);
+    if (n > hh->Nt) return fail(hh, NUFI_B200_ERR_RANGE, "Time-step out of range.");
+    if (derivative_axis < -1 || derivative_axis >= hh->dim) return fail(hh, NUFI_B200_ERR_ARG, "derivative axis must be -1 (value) or < dim");
+    if (npts == 0) return NUFI_B200_OK;
+    if (!points_host || !values_host) return fail(hh, NUFI_B200_ERR_ARG, "points / values is NULL");
+    if (!hh->level_valid[n]) return fail(hh, NUFI_B200_ERR_RANGE, "eval_field: level was never uploaded or computed");
+    const size_t w = static_cast<size_t>(hh->dim);
+    DeviceScratch d;
+    if (cudaMalloc(&d.p, sizeof(double) * npts * (w + 1)) != cudaSuccess) return fail(hh, NUFI_B200_ERR_ALLOC, "cudaMalloc of the sample points failed");
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(d.p, points_host, sizeof(double) * npts * w, cudaMemcpyHostToDevice, hh->stream));
+    const double *level = hh->d_raw ? hh->d_raw + n * hh->raw_stride : hh->d_hist + n * hh->level_stride; // reference layout
+    int rc = launch_sample_field(hh, level, derivative_axis, npts, d.p, d.p + npts * w);
+    if (rc) return rc;
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(values_host, d.p + npts * w, sizeof(double) * npts, cudaMemcpyDeviceToHost, hh->stream));
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    return NUFI_B200_OK;
+}
+
 int nufi_b200_sync(nufi_b200_handle *h)
 {
     ENTER(h);

@@ -25,6 +25,7 @@
 //    doubles) with value and derivative bases computed once per dimension and shared by the field components.
 #include "internal.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -649,6 +650,93 @@ __global__ void finish_metrics_kernel(const double *mpartials, unsigned grid, do
     }
 }
 
+// ---------------------------------------------------------------- sampling at arbitrary points (plots, diagnostics)
+// physical coordinate -> (cell, centred offset), the reference's wrap/locate arithmetic (nufi/fields.hpp:315-331)
+__device__ __forceinline__ void locate(double x, double x_min, double L, double L_inv, double dx_inv, int N, int &k, double &tau)
+{
+    x -= x_min;
+    x -= L * floor(x * L_inv);
+    const double kf = floor(x * dx_inv);
+    k = static_cast<int>(kf);
+    tau = (x * dx_inv - kf) - 0.5;
+    if (k >= N) { k -= N; } // x rounded up to exactly L
+    if (k < 0) k = 0;
+}
+
+struct SampleParams
+{
+    BtParams P;
+    double Lx, Ly, Lz, Lx_inv, Ly_inv, Lz_inv, dx_inv, dy_inv, dz_inv;
+    const double *pts; // [npts][2*dim]: x.., v..
+    double *out;
+    size_t npts;
+    int with_first_half_kick; // 1: eval_f (nufi/rho.hpp:63-96, 234-281, 369-426), 0: eval_ftilda
+};
+
+// f(t_n, x, v) at arbitrary phase-space points: one thread per point, history read from global memory.
+template <int DIM, bool XPP> __global__ void sample_f_kernel(const __grid_constant__ SampleParams S)
+{
+    const BtParams &P = S.P;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < S.npts; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const double *q = S.pts + i * 2 * DIM;
+        Point<DIM> p;
+        locate(q[0], P.x_min, S.Lx, S.Lx_inv, S.dx_inv, P.Nx, p.cell[0], p.tau[0]);
+        if constexpr (DIM >= 2) locate(q[1], P.y_min, S.Ly, S.Ly_inv, S.dy_inv, P.Ny, p.cell[1], p.tau[1]);
+        if constexpr (DIM >= 3) locate(q[2], P.z_min, S.Lz, S.Lz_inv, S.dz_inv, P.Nz, p.cell[2], p.tau[2]);
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) p.vel[d] = q[DIM + d];
+        if (P.first_level >= 0) slow_trace<DIM, XPP>(p, P); // robust path: true modulo wrap, any jump length
+        const double x = P.x_min + (p.cell[0] + (0.5 + p.tau[0])) * P.dx;
+        double f;
+        if constexpr (DIM == 1) f = f0_1d(P, x, p.vel[0]);
+        else if constexpr (DIM == 2) f = f0_2d(P, x, P.y_min + (p.cell[1] + (0.5 + p.tau[1])) * P.dy, p.vel[0], p.vel[1]);
+        else
+            f = f0_3d(P, x, P.y_min + (p.cell[1] + (0.5 + p.tau[1])) * P.dy, P.z_min + (p.cell[2] + (0.5 + p.tau[2])) * P.dz, p.vel[0],
+                      p.vel[1], p.vel[2]);
+        S.out[i] = f;
+    }
+}
+
+struct FieldSampleParams
+{
+    int dim, Nx, Ny, Nz, der; // der: -1 value, 0/1/2 first derivative along x/y/z
+    double x_min, y_min, z_min, Lx, Ly, Lz, Lx_inv, Ly_inv, Lz_inv, dx_inv, dy_inv, dz_inv;
+    const double *level; // reference-format level: halo, row stride Nx+3
+    const double *pts;   // [npts][dim]
+    double *out;
+    size_t npts;
+};
+
+// phi_n or one first derivative at arbitrary points (nufi/fields.hpp eval<real,order,dx,dy,dz>).
+__global__ void sample_field_kernel(const __grid_constant__ FieldSampleParams S)
+{
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < S.npts; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const double *q = S.pts + i * S.dim;
+        int k[3] = {0, 0, 0};
+        double tau[3] = {0, 0, 0};
+        locate(q[0], S.x_min, S.Lx, S.Lx_inv, S.dx_inv, S.Nx, k[0], tau[0]);
+        if (S.dim >= 2) locate(q[1], S.y_min, S.Ly, S.Ly_inv, S.dy_inv, S.Ny, k[1], tau[1]);
+        if (S.dim >= 3) locate(q[2], S.z_min, S.Lz, S.Lz_inv, S.dz_inv, S.Nz, k[2], tau[2]);
+        double W[3][4]; // per dimension: basis values (N_a) or derivatives (N'_a * dx_inv)
+        const double inv[3] = {S.dx_inv, S.dy_inv, S.dz_inv};
+        for (int d = 0; d < 3; ++d) {
+            double N[4], D[4];
+            basis4(tau[d], N, D);
+            for (int a = 0; a < 4; ++a) W[d][a] = d >= S.dim ? (a == 0 ? 1.0 : 0.0) : (S.der == d ? D[a] * 0.5 * inv[d] : N[a] * (1.0 / 6.0));
+        }
+        const int sy = S.Nx + 3, sz = sy * (S.Ny + 3);
+        const int nb = S.dim >= 2 ? 4 : 1, nc = S.dim >= 3 ? 4 : 1;
+        double r = 0;
+        for (int c = 0; c < nc; ++c)
+            for (int b = 0; b < nb; ++b) {
+                const double *row = S.level + static_cast<size_t>(k[2] + c) * sz + static_cast<size_t>(k[1] + b) * sy + k[0];
+                const double rv = fma(row[3], W[0][3], fma(row[2], W[0][2], fma(row[1], W[0][1], row[0] * W[0][0])));
+                r = fma(rv, W[1][b] * W[2][c], r);
+            }
+        S.out[i] = r;
+    }
+}
+
 template <int DIM, int ILP, bool STAGED, bool POW2, bool XPP>
 cudaError_t launch_variant(const BtParams &P, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
 {
@@ -872,6 +960,60 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
         finish_metrics_kernel<<<1, 32, 0, h->stream>>>(h->d_mpartials, grid, h->d_metrics);
         NUFI_CUDA_CHECK(h, cudaGetLastError());
     }
+    h->launches += 1;
+    return NUFI_B200_OK;
+}
+
+// fills the geometry / f0 part of BtParams shared by every launch
+static void fill_common(const Handle *h, BtParams &P)
+{
+    const nufi_b200_config3d &c = h->c;
+    P.dim = h->dim;
+    P.Nx = static_cast<int>(c.Nx); P.Ny = static_cast<int>(c.Ny); P.Nz = static_cast<int>(c.Nz);
+    P.Nu = static_cast<int>(c.Nu); P.Nv = static_cast<int>(c.Nv); P.Nw = static_cast<int>(c.Nw);
+    P.sx = h->sx; P.sxy = h->sxy;
+    P.hist = h->d_hist;
+    P.level_bytes = static_cast<unsigned>(h->level_stride * 8);
+    P.ncx = -(c.dt * c.dx_inv); P.ncy = -(c.dt * c.dy_inv); P.ncz = -(c.dt * c.dz_inv);
+    const double scale = h->dim == 2 ? 12.0 : 72.0;
+    P.gx = -c.dt * c.dx_inv / scale / (h->xpp ? 3.0 : 1.0); P.gy = -c.dt * c.dy_inv / scale; P.gz = -c.dt * c.dz_inv / scale;
+    P.x_min = c.x_min; P.y_min = c.y_min; P.z_min = c.z_min;
+    P.dx = c.dx; P.dy = c.dy; P.dz = c.dz;
+    P.f0_kind = h->f0.kind;
+    for (int i = 0; i < 4; ++i) P.f0p[i] = h->f0.p[i];
+}
+
+int launch_sample_f(Handle *h, size_t n, size_t npts, const double *d_pts, double *d_out, bool full)
+{
+    SampleParams S{};
+    fill_common(h, S.P);
+    const nufi_b200_config3d &c = h->c;
+    S.P.metrics = full ? 1 : 0;
+    S.P.first_level = full ? (n == 0 ? -1 : static_cast<int>(n)) : static_cast<int>(n) - 1;
+    S.Lx = c.Lx; S.Ly = c.Ly; S.Lz = c.Lz; S.Lx_inv = c.Lx_inv; S.Ly_inv = c.Ly_inv; S.Lz_inv = c.Lz_inv;
+    S.dx_inv = c.dx_inv; S.dy_inv = c.dy_inv; S.dz_inv = c.dz_inv;
+    S.pts = d_pts; S.out = d_out; S.npts = npts; S.with_first_half_kick = full ? 1 : 0;
+    const unsigned blocks = static_cast<unsigned>(std::min<size_t>((npts + 127) / 128, 148 * 8));
+    if (h->dim == 1) sample_f_kernel<1, false><<<blocks, 128, 0, h->stream>>>(S);
+    else if (h->dim == 2) { if (h->xpp) sample_f_kernel<2, true><<<blocks, 128, 0, h->stream>>>(S); else sample_f_kernel<2, false><<<blocks, 128, 0, h->stream>>>(S); }
+    else { if (h->xpp) sample_f_kernel<3, true><<<blocks, 128, 0, h->stream>>>(S); else sample_f_kernel<3, false><<<blocks, 128, 0, h->stream>>>(S); }
+    NUFI_CUDA_CHECK(h, cudaGetLastError());
+    h->launches += 1;
+    return NUFI_B200_OK;
+}
+
+int launch_sample_field(Handle *h, const double *d_ref_level, int der, size_t npts, const double *d_pts, double *d_out)
+{
+    const nufi_b200_config3d &c = h->c;
+    FieldSampleParams S{};
+    S.dim = h->dim; S.Nx = static_cast<int>(c.Nx); S.Ny = static_cast<int>(c.Ny); S.Nz = static_cast<int>(c.Nz); S.der = der;
+    S.x_min = c.x_min; S.y_min = c.y_min; S.z_min = c.z_min;
+    S.Lx = c.Lx; S.Ly = c.Ly; S.Lz = c.Lz; S.Lx_inv = c.Lx_inv; S.Ly_inv = c.Ly_inv; S.Lz_inv = c.Lz_inv;
+    S.dx_inv = c.dx_inv; S.dy_inv = c.dy_inv; S.dz_inv = c.dz_inv;
+    S.level = d_ref_level; S.pts = d_pts; S.out = d_out; S.npts = npts;
+    const unsigned blocks = static_cast<unsigned>(std::min<size_t>((npts + 127) / 128, 148 * 8));
+    sample_field_kernel<<<blocks, 128, 0, h->stream>>>(S);
+    NUFI_CUDA_CHECK(h, cudaGetLastError());
     h->launches += 1;
     return NUFI_B200_OK;
 }

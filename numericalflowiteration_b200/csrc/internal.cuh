@@ -131,7 +131,10 @@ int ev_drain(Handle *h);                                          // blocking: f
 // backtrace.cu
 // defer_finish: leave the slot reduction to the field tail (fused step); otherwise finish_rho_kernel is launched
 int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool metrics, bool defer_finish = false);
-int launch_finish(Handle *h); // runs the pending slot reduction into d_rho_partial / d_rho_full
+int launch_finish(Handle *h);
+// sampling at arbitrary points (device pointers): f / ftilda at phase-space points, phi or a first derivative at positions
+int launch_sample_f(Handle *h, size_t n, size_t npts, const double *d_pts, double *d_out, bool full);
+int launch_sample_field(Handle *h, const double *d_ref_level, int der, size_t npts, const double *d_pts, double *d_out); // runs the pending slot reduction into d_rho_partial / d_rho_full
 // tail.cu
 int tail_init(Handle *h);
 void tail_destroy(Handle *h);

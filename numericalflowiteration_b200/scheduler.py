@@ -146,9 +146,31 @@ class CudaScheduler:
         return out
 
     def upload_history(self, coeffs: np.ndarray, n_levels: int) -> None:
+        """Levels 0..n_levels-1 from a host history (restart from a checkpoint)."""
         coeffs = np.ascontiguousarray(coeffs, dtype=np.float64).ravel()
-        for m in range(n_levels):
-            self.upload_phi(m, coeffs)
+        if coeffs.size < n_levels * self.stride_t:
+            raise RangeError("host history holds fewer than n_levels levels")
+        self._ck(self._L.nufi_b200_upload_history(self._h, n_levels, _ptr(coeffs)))
+
+    def download_history(self, n_levels: int) -> np.ndarray:
+        """Levels 0..n_levels-1 in the reference layout: the complete simulation state (checkpoint)."""
+        out = np.empty(n_levels * self.stride_t)
+        self._ck(self._L.nufi_b200_download_history(self._h, n_levels, _ptr(out)))
+        return out
+
+    def eval_f(self, n: int, points: np.ndarray, full: bool = True) -> np.ndarray:
+        """f(t_n, x, v) (full=True: eval_f) or ftilda (full=False) at phase-space points [npts, 2*dim]."""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 2 * self.dim)
+        out = np.empty(len(pts))
+        self._ck(self._L.nufi_b200_eval_f(self._h, n, len(pts), _ptr(pts), _ptr(out), int(full)))
+        return out
+
+    def eval_field(self, n: int, points: np.ndarray, derivative_axis: int = -1) -> np.ndarray:
+        """phi_n (derivative_axis=-1) or its first derivative along an axis at positions [npts, dim]."""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, self.dim)
+        out = np.empty(len(pts))
+        self._ck(self._L.nufi_b200_eval_field(self._h, n, derivative_axis, len(pts), _ptr(pts), _ptr(out)))
+        return out
 
     def sync(self) -> None:
         self._ck(self._L.nufi_b200_sync(self._h))

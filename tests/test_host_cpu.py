@@ -184,3 +184,42 @@ int main(){
     c1, c2, c3 = Config1D(), Config2D(), Config3D()
     assert [int(x) for x in out[:6]] == [256, 512, 1600, 800, 50, 35 * 8]
     assert float(out[6]) == c1.dx and float(out[7]) == c2.dv and float(out[8]) == c3.x_max
+
+
+def test_history_file_formats_roundtrip(tmp_path):
+    """Binary checkpoint and the reference's two text formats (isolated-step harness, 1d driver dump), Python and C++."""
+    from numericalflowiteration_b200 import history_io
+
+    conf = Config3D(Nx=5, Ny=4, Nz=6, Nt=3)
+    st = stride_t(conf)
+    rng = np.random.default_rng(5)
+    coeffs = rng.standard_normal(4 * st) * 10.0 ** rng.integers(-12, 3, size=4 * st)
+    history_io.write_binary(tmp_path / "h.bin", conf, coeffs, 4)
+    hdr, back = history_io.read_binary(tmp_path / "h.bin")
+    assert np.array_equal(back, coeffs) and hdr["n_levels"] == 4 and (hdr["Nx"], hdr["Ny"], hdr["Nz"]) == (5, 4, 6) and hdr["dt"] == conf.dt
+    history_io.write_text_isolated(tmp_path / "h.txt", conf, coeffs, 4)
+    lines = open(tmp_path / "h.txt").read().splitlines()
+    assert lines[:7] == ["Nt = 3", f"dt = {conf.dt:f}", "Nx = 5", "Ny = 4", "Nz = 6", "order = 4", ""]  # isolated.cpp:64-70
+    assert np.array_equal(history_io.read_text(tmp_path / "h.txt", 4 * st, header_lines=7), coeffs)
+    history_io.write_text_plain(tmp_path / "p.txt", coeffs)
+    assert np.array_equal(history_io.read_text(tmp_path / "p.txt", 4 * st), coeffs)
+    # the C++ header reads what Python wrote and writes what Python reads
+    src = r'''
+#include <nufi/history_io.hpp>
+#include <cstdio>
+int main(int argc, char** argv){
+  std::vector<double> c, t;
+  auto h = nufi::history_io::read_binary(argv[1], c);
+  nufi::history_io::read_text(argv[2], 7, c.size(), t);
+  if (t != c) return 3;
+  nufi::history_io::write_binary(argv[3], h, c.data());
+  nufi::history_io::write_text_isolated(argv[4], h, c.data());
+  std::printf("%u %u %llu %zu\n", h.dim, h.order, (unsigned long long)h.n_levels, nufi::history_io::stride_t(h));
+  return 0; }'''
+    open(tmp_path / "t.cpp", "w").write(src)
+    subprocess.run(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-o", str(tmp_path / "t"), str(tmp_path / "t.cpp")], check=True)
+    out = subprocess.run([str(tmp_path / "t"), str(tmp_path / "h.bin"), str(tmp_path / "h.txt"), str(tmp_path / "h2.bin"), str(tmp_path / "h2.txt")],
+                         capture_output=True, text=True, check=True).stdout.split()
+    assert [int(x) for x in out] == [3, 4, 4, st]
+    assert open(tmp_path / "h2.bin", "rb").read() == open(tmp_path / "h.bin", "rb").read()
+    assert np.array_equal(history_io.read_text(tmp_path / "h2.txt", 4 * st, header_lines=7), coeffs)
