@@ -464,7 +464,9 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1) backtrace
             if (!P.metrics) flush_tile(cur_tile);
             cur_tile = tile;
         }
-        const unsigned jc = jr * W + warp;
+        // warp-unit of this warp: interleaved (default) = the warps of a round and the points of a thread are spread evenly
+        // over the velocity range, so every CTA sees the same mix of fast/trapped orbits (equal bank-conflict load)
+        const unsigned jc = P.interleave ? jr + warp * P.rpt : jr * W + warp;
         if (jc >= P.upt) { // no unit for this warp in this round: keep the stage protocol going
             if constexpr (STAGED) {
                 for (int c = c_hi; c >= 0; --c) {
@@ -494,7 +496,8 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1) backtrace
         double v0[ILP][DIM]; // starting velocities (metrics need them; the slow path restarts from them)
 #pragma unroll
         for (int i = 0; i < ILP; ++i) {
-            unsigned long long j = static_cast<unsigned long long>(jc) * ILP + i;
+            unsigned long long j = P.interleave ? static_cast<unsigned long long>(jc) + static_cast<unsigned long long>(i) * P.upt
+                                                : static_cast<unsigned long long>(jc) * ILP + i;
             ok[i] = node_ok && j < P.Nvel;
             const unsigned long long q = l * P.Nvel + j;
             ok[i] = ok[i] && q >= P.q_begin && q < P.q_end;
@@ -902,6 +905,7 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     P.R = static_cast<unsigned>(R64);
     P.rpc = (P.R + grid - 1) / grid;
     P.Tmax = (P.rpc - 1) / P.rpt + 2;
+    P.interleave = env_int("NUFI_B200_INTERLEAVE", 1) ? 1 : 0;
     const unsigned threads = (P.W + (staged ? 1 : 0)) * 32;
     const size_t smem_bytes = kSmemFixed + (staged ? static_cast<size_t>(P.stages) * P.stage_bytes : 0);
 

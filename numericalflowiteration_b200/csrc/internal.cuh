@@ -44,6 +44,7 @@ struct BtParams
     unsigned int R;                  // CTA-rounds in total = rpt * n_tiles
     unsigned int rpc;                // CTA-rounds per CTA = ceil(R / grid)
     unsigned int Tmax;               // slots per CTA (tiles one CTA can touch)
+    int interleave;                  // 1: warp-unit jc = jr + warp*rpt, point i of a thread at velocity jc + i*upt (balanced mix)
     double *slots;                   // [grid][Tmax][32]                (rho)
     double *mpartials;               // [grid][4]                       (metrics)
     double mweight;

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Condense `ncu -i X.ncu-rep --page raw --csv` into the handful of counters DESIGN.md / profiles/README.md quote.
+
+    python tools/ncu_summary.py gpurun_out/prof_C2.ncu-rep [more.ncu-rep ...] > profiles/rNNx_ncu_full_summary.csv
+"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.per_cycle_active", "sm__cycles_elapsed.max",
+    "sm__cycles_active.avg", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum", "smsp__warps_eligible.avg.per_cycle_active",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+]
+
+
+def main():
+    w = csv.writer(sys.stdout)
+    w.writerow(["report", "kernel", "metric", "unit", "value"])
+    for rep in sys.argv[1:]:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        hdr, units = rows[0], rows[1]
+        for vals in rows[2:]:
+            d = dict(zip(hdr, zip(units, vals)))
+            name = d.get("Kernel Name", ("", "?"))[1]
+            for k in KEYS:
+                if k in d:
+                    w.writerow([rep.split("/")[-1], name, k, d[k][0], d[k][1]])
+
+
+if __name__ == "__main__":
+    main()
