@@ -180,7 +180,7 @@ def run_reference_arm(args):
 class GpuRunner:
     """One rank's scheduler + (for N > 1) the NCCL all-reduce of the partial rho."""
 
-    def __init__(self, conf, f0, rank, world, torch, dist):
+    def __init__(self, conf, f0, rank, world, torch, dist, exchange="peer"):
         from numericalflowiteration_b200 import CudaScheduler, partition
 
         self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
@@ -188,15 +188,40 @@ class GpuRunner:
         self.stream = torch.cuda.Stream()
         self.s.set_stream(self.stream.cuda_stream)
         self.q0, self.q1 = partition(self.s.n_quad, world, rank)
+        self.exchange, self.exchange_note = "single", None
         if world > 1:
             from numericalflowiteration_b200.distributed import _alias_device_f64
 
             self.rho_t = _alias_device_f64(torch, self.s.rho_device_ptr(), self.s.n_nodes)
+            self.exchange = "nccl"
+            if exchange == "peer":  # map every rank's exchange buffer into every rank (CUDA IPC); all ranks or none
+                ok, why = 1, None
+                try:
+                    mine = self.s.peer_export(world)
+                except Exception as e:  # noqa: BLE001
+                    ok, why, mine = 0, repr(e), b"\0" * 64
+                handles = [None] * world
+                dist.all_gather_object(handles, mine)
+                if ok:
+                    try:
+                        self.s.peer_attach(rank, world, b"".join(handles))
+                    except Exception as e:  # noqa: BLE001
+                        ok, why = 0, repr(e)
+                t = torch.tensor([ok], device="cuda", dtype=torch.int32)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                if int(t.item()) == 1:
+                    self.exchange = "peer-memory"
+                else:
+                    self.exchange_note = f"peer-memory exchange unavailable ({why or 'failed on another rank'}); NCCL all-reduce used"
+                    print(f"[bench rank {rank}] {self.exchange_note}", file=sys.stderr)
 
     def step(self, n):
-        """Fused step, no host round trip.  N > 1: local shard -> NCCL all-reduce (in place, device) -> replicated tail."""
+        """Fused step, no host round trip.  N > 1: local shard -> exchange of the partial rho (stores into peer memory fused
+        into the slot reduction + flags; or NCCL all-reduce in place) -> replicated tail."""
         if self.world == 1:
             self.s.step(n)
+        elif self.exchange == "peer-memory":
+            self.s.peer_step(n)
         else:
             self.s.compute_rho(n, self.q0, self.q1)
             with self.torch.cuda.stream(self.stream):
@@ -313,7 +338,7 @@ def run_gpu_arm(args):
     conf, f0, depth, desc = make_workload(args.workload, world)
     n = args.depth or depth
     dim = conf.dim
-    runner = GpuRunner(conf, f0, rank, world, torch, dist)
+    runner = GpuRunner(conf, f0, rank, world, torch, dist, exchange=args.exchange)
     s = runner.s
     nq = n_quad(conf)
     flush = torch.empty(L2_FLUSH_BYTES // 8, dtype=torch.float64, device="cuda")
@@ -324,6 +349,8 @@ def run_gpu_arm(args):
 
     sampler = ClockSampler(local) if rank == 0 else None
     m = measure_gpu(runner, n, args.steps, args.warmup, flush, torch, dist, sampler)
+    if runner.exchange == "peer-memory" and s.peer_timed_out():
+        raise SystemExit("bench.py: a wait for a peer's rho flag timed out -- the multi-GPU result would be invalid")
     psteps = float(nq) * n  # whole job, all ranks
     value = psteps * args.steps / (m["t_ms"] * 1e-3)
     variant = s.last_variant
@@ -381,7 +408,10 @@ def run_gpu_arm(args):
             "config": {"workload": desc, "depth_n": n, "point_steps_per_step": psteps, "n_quad": nq,
                        "history": f"built on the device by {n} free-running fused steps ({t_hist:.2f} s)",
                        "l2": "flushed between timed steps (256 MiB fill, untimed; steps timed individually with CUDA events)",
-                       "parallelism": f"quadrature points sharded over {world} GPU(s), NCCL all-reduce of rho" if world > 1 else "1 GPU"},
+                       "parallelism": (f"quadrature points sharded over {world} GPU(s); rho exchange: " +
+                                       ("stores into NVLink peer memory fused into the slot-reduction and tail kernels (no collective call)"
+                                        if runner.exchange == "peer-memory" else "NCCL all-reduce")) if world > 1 else "1 GPU",
+                       "exchange": runner.exchange, "exchange_note": runner.exchange_note},
             "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
             "e2e": {"value": e2e_value, "unit": "point-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps,
@@ -447,6 +477,8 @@ def main():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--depth", type=int, default=0, help="history depth n of the timed step (default: per workload)")
     ap.add_argument("--cpu-budget", type=float, default=3.0, help="seconds of wall time for the cpu_baseline sample")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the partial rho is exchanged (peer = stores into NVLink peer memory fused into the kernels)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", dest="extras", action="store_false")
     args = ap.parse_args()

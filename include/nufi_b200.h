@@ -170,9 +170,26 @@ int nufi_b200_rho_device(nufi_b200_handle *h, double **d_rho);
  * rho = 1 + sum, solve, interpolate, store level n, record energy[n].  Asynchronous. */
 int nufi_b200_field_tail_device(nufi_b200_handle *h, size_t n, const double *d_rho_partial_sum);
 
+/* ---- multi-GPU step with the exchange of the partial rho FUSED into the path's kernels, over NVLink/NVSwitch peer memory
+ *      (replaces cuda_kernel::download_rho + host add, nufi/cuda_kernel.cu:135-145, nufi/cuda_scheduler.hpp:113-118, and the
+ *      MPI_Allreduce of bin/test_nufi_gpu_3d.cpp:158).  One process per GPU: every rank calls peer_export (allocates its exchange
+ *      buffer, returns a 64-byte CUDA IPC handle), the host layer all-gathers the handles (rank order), every rank calls
+ *      peer_attach.  peer_step(n) = backtrace of this rank's share of the flat q range (the reference's split,
+ *      nufi/cuda_scheduler.hpp:88-111) -> slot reduction that STORES the partial rho into every GPU's buffer and releases a
+ *      flag there -> field tail that acquires all ranks' flags and adds the contributions in rank order (bit-identical on all
+ *      GPUs) -> level n.  Asynchronous, no collective call, no host synchronisation.  All ranks must call peer_step the same
+ *      number of times; synchronise all ranks (host barrier) before peer_detach / destroy.  peer_status: blocking; *timed_out
+ *      = 1 if a wait for a peer's flag ever gave up (a rank died or skipped a step; results are then invalid). ---- */
+#define NUFI_B200_PEER_HANDLE_BYTES 64
+int nufi_b200_peer_export(nufi_b200_handle *h, int world, void *ipc_handle);
+int nufi_b200_peer_attach(nufi_b200_handle *h, int rank, int world, const void *ipc_handles /* world x 64 bytes, rank order */);
+int nufi_b200_peer_step(nufi_b200_handle *h, size_t n);
+int nufi_b200_peer_status(nufi_b200_handle *h, int *timed_out);
+int nufi_b200_peer_detach(nufi_b200_handle *h);
+
 /* ---- several GPUs driven by ONE process (the reference's cuda_scheduler shape: one host thread, all visible devices,
  *      nufi/cuda_scheduler.hpp:43-63).  A group ties one handle per device together with NCCL communicators
- *      (ncclCommInitAll; libnccl.so.2 is loaded on first use).  group_step = per device: backtrace of its contiguous
+ *      (ncclCommInitAll; libnccl.so.2 is loaded on first use) or with direct peer access.  group_step = per device: backtrace of its contiguous
  *      share of the flat q range (the reference's split, cuda_scheduler.hpp:88-111) -> ncclAllReduce(sum) of the
  *      partial rho in place on the devices (replaces download_rho + host add + MPI_Allreduce,
  *      bin/test_nufi_gpu_3d.cpp:154-158) -> the replicated field tail on every device.  Asynchronous. ---- */
@@ -181,6 +198,10 @@ int nufi_b200_group_create(nufi_b200_handle *const *handles, int n_handles, nufi
 void nufi_b200_group_destroy(nufi_b200_group *g);
 int nufi_b200_group_step(nufi_b200_group *g, size_t n);
 int nufi_b200_group_sync(nufi_b200_group *g);
+/* how group_step exchanges the partial rho: 0 = peer memory, fused into the kernels as in peer_step (default whenever every
+ * device of the group can map every other one), 1 = NCCL all-reduce between backtrace and tail.  group_exchange names it. */
+int nufi_b200_group_set_exchange(nufi_b200_group *g, int mode);
+const char *nufi_b200_group_exchange(const nufi_b200_group *g);
 const char *nufi_b200_group_last_error(const nufi_b200_group *g);
 
 /* ---- introspection used by bench.py / tests ---- */

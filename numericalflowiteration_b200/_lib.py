@@ -23,6 +23,8 @@ SYMBOLS = [
     "nufi_b200_set_tail_variant", "nufi_b200_last_tail_variant", "nufi_b200_measure_fp64_peak", "nufi_b200_version",
     "nufi_b200_group_create", "nufi_b200_group_destroy", "nufi_b200_group_step", "nufi_b200_group_sync",
     "nufi_b200_group_last_error", "nufi_b200_device_count", "nufi_b200_device_of",
+    "nufi_b200_peer_export", "nufi_b200_peer_attach", "nufi_b200_peer_step", "nufi_b200_peer_status", "nufi_b200_peer_detach",
+    "nufi_b200_group_set_exchange", "nufi_b200_group_exchange",
 ]
 
 _lib = None
@@ -65,6 +67,9 @@ def load() -> C.CDLL:
         "eval_field": [vp, sz, i, sz, vp, vp],
         "poisson_solve": [vp, vp, dp], "interpolate": [vp, vp, vp], "device_count": [C.POINTER(i)], "device_of": [vp],
         "group_create": [C.POINTER(vp), i, C.POINTER(vp)], "group_step": [vp, sz], "group_sync": [vp],
+        "group_set_exchange": [vp, i],
+        "peer_export": [vp, i, vp], "peer_attach": [vp, i, i, vp], "peer_step": [vp, sz], "peer_status": [vp, C.POINTER(i)],
+        "peer_detach": [vp],
     }.items():
         f = getattr(L, "nufi_b200_" + name)
         f.argtypes = args
@@ -79,6 +84,8 @@ def load() -> C.CDLL:
     L.nufi_b200_group_destroy.restype = None
     L.nufi_b200_group_last_error.argtypes = [vp]
     L.nufi_b200_group_last_error.restype = C.c_char_p
+    L.nufi_b200_group_exchange.argtypes = [vp]
+    L.nufi_b200_group_exchange.restype = C.c_char_p
     L.nufi_b200_version.restype = C.c_char_p
     _lib = L
     return L

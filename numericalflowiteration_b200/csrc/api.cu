@@ -65,6 +65,7 @@ void free_all(Handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     tail_destroy(h);
+    peer_free(h);
     cudaFree(h->d_hist); cudaFree(h->d_raw);
     cudaFree(h->d_rho_partial); cudaFree(h->d_rho_full); cudaFree(h->d_partials);
     cudaFree(h->d_metrics); cudaFree(h->d_mpartials); cudaFree(h->d_energy); cudaFree(h->d_stage);

@@ -644,6 +644,56 @@ __global__ void __launch_bounds__(256) finish_rho_kernel(const __grid_constant__
     }
 }
 
+// peer-memory primitives: system-scope release / acquire on the exchange flags
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// finish_rho_kernel fused with the peer exchange (multi-GPU step): the tile's rho values are stored straight into the
+// exchange buffer of EVERY GPU (own one included; remote stores travel over NVLink), and the last block to finish releases
+// this rank's flag on every GPU.  grid = max(n_tiles, 1) blocks: a rank without work only raises its flags.
+__global__ void __launch_bounds__(256) finish_push_kernel(const __grid_constant__ FinishParams F, const __grid_constant__ PeerPush X)
+{
+    __shared__ double part[8][32];
+    const unsigned tile = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned wj = threadIdx.x >> 5;
+    if (tile < F.n_tiles) {
+        const unsigned b_lo = (tile * F.rpt) / F.rpc;
+        const unsigned b_hi = ((tile + 1) * F.rpt - 1) / F.rpc;
+        double sum = 0;
+        for (unsigned b = b_lo + wj; b <= b_hi; b += 8) {
+            const unsigned t_first = (b * F.rpc) / F.rpt;
+            sum += F.slots[(static_cast<size_t>(b) * F.Tmax + (tile - t_first)) * 32 + lane];
+        }
+        part[wj][lane] = sum;
+        __syncthreads();
+        if (wj == 0) {
+            double tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += part[w][lane];
+            const unsigned long long l = F.l_first + static_cast<unsigned long long>(tile) * 32 + lane;
+            if (l <= F.l_last) {
+                const double val = -F.dV * tot;
+                F.rho_partial[l] = val;
+                if (F.rho_full) F.rho_full[l] = 1 - F.dV * tot;
+                for (int p = 0; p < X.world; ++p) X.data[p][l] = val;
+            }
+        }
+    }
+    __threadfence_system(); // this block's remote stores are visible system-wide before its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(X.ticket, 1u);
+        if (t == gridDim.x - 1) { // every block has stored and fenced
+            *X.ticket = 0;
+            __threadfence_system();
+            for (int p = 0; p < X.world; ++p) st_release_sys(X.flag[p], X.epoch);
+        }
+    }
+}
+
 __global__ void finish_metrics_kernel(const double *mpartials, unsigned grid, double *metrics)
 {
     if (threadIdx.x < 4) {
@@ -1022,10 +1072,22 @@ int launch_sample_field(Handle *h, const double *d_ref_level, int der, size_t np
     return NUFI_B200_OK;
 }
 
+int launch_flag_only_push(Handle *h)
+{
+    FinishParams F{};
+    F.n_tiles = 0;
+    h->fin = F;
+    h->fin_pending = true;
+    h->fin_push = true;
+    return launch_finish(h);
+}
+
 int launch_finish(Handle *h)
 {
     if (!h->fin_pending) return NUFI_B200_OK;
-    finish_rho_kernel<<<h->fin.n_tiles, 256, 0, h->stream>>>(h->fin);
+    if (h->fin_push) finish_push_kernel<<<h->fin.n_tiles ? h->fin.n_tiles : 1, 256, 0, h->stream>>>(h->fin, h->px.push);
+    else finish_rho_kernel<<<h->fin.n_tiles, 256, 0, h->stream>>>(h->fin);
+    h->fin_push = false;
     NUFI_CUDA_CHECK(h, cudaGetLastError());
     h->fin_pending = false;
     h->launches += 1;

@@ -63,6 +63,80 @@ struct FinishParams
     unsigned int rpt, rpc, Tmax, n_tiles;
 };
 
+// ----------------------------------------------------------------------------------------------
+// Peer exchange of the partial rho over NVLink/NVSwitch peer memory (peer.cu).  Every GPU owns an exchange buffer
+//   [flags: 2 parities x kMaxPeers x u64][data: 2 parities x world x n_nodes doubles]
+// mapped into all peers (one process: cudaDeviceEnablePeerAccess; one process per GPU: CUDA IPC).  Per step with epoch e
+// (parity e&1) rank r STORES its partial rho straight into data[e&1][r] of every GPU, then releases flag[e&1][r] = e
+// there; the field tail of every GPU acquires the world flags and adds the contributions in rank order.
+// ----------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+constexpr size_t kPeerFlagBytes = 2 * kMaxPeers * sizeof(unsigned long long);
+
+struct PeerPush // sender side (finish_push_kernel)
+{
+    double *data[kMaxPeers];            // data[e&1][my rank] inside every GPU's exchange buffer
+    unsigned long long *flag[kMaxPeers]; // flag[e&1][my rank] inside every GPU's exchange buffer
+    int world;
+    unsigned long long epoch;
+    unsigned int *ticket;               // local last-block counter
+};
+
+struct PeerRecv // receiver side (tail_small_kernel / peer_gather_kernel)
+{
+    int world;                          // 0: not a peer step
+    const unsigned long long *flags;    // local flag[e&1][0..world)
+    const double *data;                 // local data[e&1][0..world)[n_nodes]
+    unsigned long long epoch;
+    unsigned long long l_first[kMaxPeers], l_last[kMaxPeers]; // node range each rank contributes to (first > last: none)
+    double *rho_full;                   // CPU-convention rho (1 + sum) for later downloads
+    int *status;                        // set to 1 if a flag never arrived (bounded spin)
+};
+
+#ifdef __CUDACC__
+// Receiver: thread r < world spins (bounded, ~2 s) until rank r's flag of this epoch has arrived.  Call from all threads
+// of the block and follow with __syncthreads(); read the data with __ldcg (L2: the peers wrote it behind L1's back).
+__device__ __forceinline__ void peer_wait_all(const PeerRecv &X)
+{
+    if (static_cast<int>(threadIdx.x) < X.world) {
+        const unsigned long long *f = X.flags + threadIdx.x;
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= X.epoch) break;
+            if (clock64() - t0 > (1ll << 32)) { // a peer never pushed: do not hang the GPU, report through the status word
+                *X.status = 1;
+                break;
+            }
+        }
+    }
+}
+
+// rho[l] = 1 + sum over the ranks that cover node l, in rank order (identical on every GPU)
+__device__ __forceinline__ double peer_sum(const PeerRecv &X, size_t n_nodes, unsigned long long l)
+{
+    double sum = 0;
+    for (int r = 0; r < X.world; ++r)
+        if (l >= X.l_first[r] && l <= X.l_last[r]) sum += __ldcg(X.data + static_cast<size_t>(r) * n_nodes + l);
+    return 1 + sum;
+}
+#endif
+
+struct PeerState
+{
+    int world = 0, rank = -1;
+    bool ipc = false;                   // peer buffers opened through CUDA IPC (must be closed), else direct peer access
+    unsigned char *xb = nullptr;        // local exchange buffer
+    size_t xb_bytes = 0;
+    unsigned char *peer_xb[kMaxPeers] = {};
+    unsigned long long epoch = 0;
+    unsigned int *d_ticket = nullptr;
+    int *d_status = nullptr;
+    PeerPush push{};                    // of the step being launched
+    PeerRecv recv{};
+};
+
 struct Handle
 {
     int dim = 0, order = 4, device = 0;
@@ -107,6 +181,8 @@ struct Handle
     uint64_t bt_count = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
+    PeerState px;
+    bool fin_push = false;       // the pending slot reduction also pushes to the peers (finish_push_kernel)
     int variant_force = 0;
     const char *last_variant = "none";
     char variant_buf[64] = {0};
@@ -140,7 +216,14 @@ int launch_sample_field(Handle *h, const double *d_ref_level, int der, size_t np
 int tail_init(Handle *h);
 void tail_destroy(Handle *h);
 // d_rho_full == nullptr: take rho from the pending slot reduction of the last backtrace launch
-int tail_run(Handle *h, size_t n, const double *d_rho_full);
+// from_peer: rho = 1 + sum over ranks of the exchange buffer (h->px.recv), waited for inside the tail
+int tail_run(Handle *h, size_t n, const double *d_rho_full, bool from_peer = false);
+// peer.cu
+void peer_free(Handle *h);
+int peer_alloc(Handle *h, int world);
+int peer_prepare_step(Handle *h);                 // next epoch: fills h->px.push / h->px.recv
+int launch_peer_gather(Handle *h);                // exchange buffer -> d_rho_full (large grids, cuFFT tail)
+int launch_flag_only_push(Handle *h);             // a rank with an empty q-range still has to raise its flags
 int tail_filter(Handle *h, const double *d_values, int mode); // 1: poisson solve, 2: interpolate; result in d_field
 int expand_field_to_stage(Handle *h);
 double *tail_energy_scratch(Handle *h);

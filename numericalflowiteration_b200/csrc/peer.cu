@@ -1,0 +1,211 @@
+// peer.cu -- the per-step exchange of the partial rho between the GPUs of one NVSwitch box, fused into the path's own kernels.
+//
+// Replaces the reference's fan-in (cuda_kernel::download_rho's blocking copy + host add per device, nufi/cuda_kernel.cu:135-145,
+// nufi/cuda_scheduler.hpp:113-118, and MPI_Allreduce on host buffers, bin/test_nufi_gpu_3d.cpp:158) -- and the NCCL all-reduce
+// this library used first -- by direct stores into peer memory:
+//   * finish_push_kernel (backtrace.cu): the slot reduction that produces this GPU's partial rho writes it into the exchange
+//     buffer of EVERY GPU (NVLink stores) and the last block releases a per-(rank, parity) epoch flag on every GPU;
+//   * the field tail (tail_small_kernel / peer_gather_kernel) acquires the `world` flags and adds the contributions in rank
+//     order, so all replicas compute bit-identical rho, phi and histories with no collective call, no extra launch for the
+//     reduction and no host synchronisation.  Two parities make the buffers safe to reuse: a rank can only write epoch e+2
+//     after its tail of e+1 saw every peer's push of e+1, which those peers issued after their tail of e had read epoch e.
+// Mapping of the peers' buffers: one process driving all GPUs (nufi_b200_group_*) enables direct peer access; one process per
+// GPU (torchrun) exchanges cudaIpcMemHandle_t through the host layer (nufi_b200_peer_export / _attach).
+#include "internal.cuh"
+
+#include <cstring>
+
+namespace nufi_b200
+{
+
+namespace
+{
+
+// exchange buffer -> d_rho_full for grids too large for the single-CTA tail (the cuFFT path reads rho from memory)
+__global__ void __launch_bounds__(256) peer_gather_kernel(const __grid_constant__ PeerRecv X, size_t n_nodes)
+{
+    peer_wait_all(X);
+    __syncthreads();
+    for (size_t l = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; l < n_nodes; l += static_cast<size_t>(gridDim.x) * blockDim.x)
+        X.rho_full[l] = peer_sum(X, n_nodes, l);
+}
+
+size_t data_offset(const Handle *h, int parity, int rank)
+{
+    return kPeerFlagBytes + (static_cast<size_t>(parity) * h->px.world + rank) * h->n_nodes * sizeof(double);
+}
+
+} // namespace
+
+void peer_free(Handle *h)
+{
+    PeerState &px = h->px;
+    if (px.ipc)
+        for (int p = 0; p < px.world; ++p)
+            if (p != px.rank && px.peer_xb[p]) cudaIpcCloseMemHandle(px.peer_xb[p]);
+    cudaFree(px.xb);
+    cudaFree(px.d_ticket);
+    cudaFree(px.d_status);
+    px = PeerState{};
+}
+
+int peer_alloc(Handle *h, int world)
+{
+    if (world < 1 || world > kMaxPeers) return fail(h, NUFI_B200_ERR_ARG, "peer exchange: world size must be 1.." + std::to_string(kMaxPeers));
+    peer_free(h);
+    PeerState &px = h->px;
+    px.world = world;
+    px.xb_bytes = kPeerFlagBytes + 2 * static_cast<size_t>(world) * h->n_nodes * sizeof(double);
+    NUFI_CUDA_CHECK(h, cudaMalloc(&px.xb, px.xb_bytes));
+    NUFI_CUDA_CHECK(h, cudaMemset(px.xb, 0, px.xb_bytes));
+    NUFI_CUDA_CHECK(h, cudaMalloc(&px.d_ticket, sizeof(unsigned int)));
+    NUFI_CUDA_CHECK(h, cudaMemset(px.d_ticket, 0, sizeof(unsigned int)));
+    NUFI_CUDA_CHECK(h, cudaMalloc(&px.d_status, sizeof(int)));
+    NUFI_CUDA_CHECK(h, cudaMemset(px.d_status, 0, sizeof(int)));
+    NUFI_CUDA_CHECK(h, cudaDeviceSynchronize()); // the zeroed flags are in place before any peer learns the address
+    return NUFI_B200_OK;
+}
+
+// Next epoch: pointers for the sender, ranges for the receiver.  The q-range split is the reference scheduler's
+// (nufi/cuda_scheduler.hpp:88-111): contiguous, the first Nquad % world shares one longer.
+int peer_prepare_step(Handle *h)
+{
+    PeerState &px = h->px;
+    if (px.world < 1 || px.rank < 0) return fail(h, NUFI_B200_ERR_ARG, "peer exchange not attached (nufi_b200_peer_attach / group)");
+    const unsigned long long e = ++px.epoch;
+    const int parity = static_cast<int>(e & 1);
+    PeerPush P{};
+    P.world = px.world;
+    P.epoch = e;
+    P.ticket = px.d_ticket;
+    for (int p = 0; p < px.world; ++p) {
+        P.data[p] = reinterpret_cast<double *>(px.peer_xb[p] + data_offset(h, parity, px.rank));
+        P.flag[p] = reinterpret_cast<unsigned long long *>(px.peer_xb[p]) + parity * kMaxPeers + px.rank;
+    }
+    PeerRecv R{};
+    R.world = px.world;
+    R.epoch = e;
+    R.flags = reinterpret_cast<const unsigned long long *>(px.xb) + parity * kMaxPeers;
+    R.data = reinterpret_cast<const double *>(px.xb + data_offset(h, parity, 0));
+    R.rho_full = h->d_rho_full;
+    R.status = px.d_status;
+    const size_t nq = h->n_nodes * h->n_vel, chunk = nq / px.world, rem = nq % px.world;
+    size_t q0 = 0;
+    for (int r = 0; r < px.world; ++r) {
+        const size_t q1 = q0 + chunk + (static_cast<size_t>(r) < rem ? 1 : 0);
+        if (q1 > q0) { R.l_first[r] = q0 / h->n_vel; R.l_last[r] = (q1 - 1) / h->n_vel; }
+        else { R.l_first[r] = 1; R.l_last[r] = 0; }
+        q0 = q1;
+    }
+    px.push = P;
+    px.recv = R;
+    return NUFI_B200_OK;
+}
+
+int launch_peer_gather(Handle *h)
+{
+    size_t blocks = (h->n_nodes + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    peer_gather_kernel<<<static_cast<unsigned>(blocks), 256, 0, h->stream>>>(h->px.recv, h->n_nodes);
+    NUFI_CUDA_CHECK(h, cudaGetLastError());
+    h->launches += 1;
+    return NUFI_B200_OK;
+}
+
+} // namespace nufi_b200
+
+using namespace nufi_b200;
+
+static inline Handle *HH(nufi_b200_handle *h) { return reinterpret_cast<Handle *>(h); }
+
+#define PEER_ENTER(h)                                                    \
+    Handle *hh = HH(h);                                                  \
+    if (!hh) return fail(nullptr, NUFI_B200_ERR_ARG, "handle is NULL");  \
+    NUFI_CUDA_CHECK(hh, cudaSetDevice(hh->device))
+
+extern "C" {
+
+int nufi_b200_peer_export(nufi_b200_handle *h, int world, void *ipc_handle)
+{
+    PEER_ENTER(h);
+    if (!ipc_handle) return fail(hh, NUFI_B200_ERR_ARG, "ipc_handle is NULL");
+    static_assert(sizeof(cudaIpcMemHandle_t) == NUFI_B200_PEER_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+    int rc = peer_alloc(hh, world);
+    if (rc) return rc;
+    cudaIpcMemHandle_t mh;
+    NUFI_CUDA_CHECK(hh, cudaIpcGetMemHandle(&mh, hh->px.xb));
+    std::memcpy(ipc_handle, &mh, sizeof(mh));
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_peer_attach(nufi_b200_handle *h, int rank, int world, const void *ipc_handles)
+{
+    PEER_ENTER(h);
+    PeerState &px = hh->px;
+    if (!px.xb || px.world != world) return fail(hh, NUFI_B200_ERR_ARG, "peer_attach: call nufi_b200_peer_export with the same world size first");
+    if (rank < 0 || rank >= world) return fail(hh, NUFI_B200_ERR_ARG, "peer_attach: rank out of range");
+    if (!ipc_handles && world > 1) return fail(hh, NUFI_B200_ERR_ARG, "ipc_handles is NULL");
+    px.rank = rank;
+    px.ipc = true;
+    for (int p = 0; p < world; ++p) {
+        if (p == rank) { px.peer_xb[p] = px.xb; continue; }
+        cudaIpcMemHandle_t mh;
+        std::memcpy(&mh, static_cast<const unsigned char *>(ipc_handles) + static_cast<size_t>(p) * sizeof(mh), sizeof(mh));
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int q = 0; q < p; ++q)
+                if (q != rank && px.peer_xb[q]) { cudaIpcCloseMemHandle(px.peer_xb[q]); px.peer_xb[q] = nullptr; }
+            px.rank = -1;
+            return fail(hh, NUFI_B200_ERR_CUDA, std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(p) + "): " + cudaGetErrorString(e));
+        }
+        px.peer_xb[p] = static_cast<unsigned char *>(ptr);
+    }
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_peer_detach(nufi_b200_handle *h)
+{
+    PEER_ENTER(h);
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    peer_free(hh);
+    return NUFI_B200_OK;
+}
+
+int nufi_b200_peer_step(nufi_b200_handle *h, size_t n)
+{
+    PEER_ENTER(h);
+    if (n > hh->Nt) return fail(hh, NUFI_B200_ERR_RANGE, "Time-step out of range.");
+    for (size_t m = 0; m < n; ++m) // validate BEFORE the epoch advances: a rank that bails out later would stall its peers
+        if (!hh->level_valid[m])
+            return fail(hh, NUFI_B200_ERR_RANGE, "peer_step: history level " + std::to_string(m) + " was never uploaded or computed");
+    int rc = peer_prepare_step(hh);
+    if (rc) return rc;
+    const PeerState &px = hh->px;
+    const size_t nq = hh->n_nodes * hh->n_vel, chunk = nq / px.world, rem = nq % px.world;
+    const size_t r = static_cast<size_t>(px.rank);
+    const size_t q0 = r * chunk + (r < rem ? r : rem), q1 = q0 + chunk + (r < rem ? 1 : 0);
+    if (q1 > q0) {
+        hh->fin_push = true;
+        rc = nufi_b200_compute_rho(h, n, q0, q1); // backtrace, then finish_push_kernel instead of finish_rho_kernel
+        hh->fin_push = false;
+    } else {
+        rc = launch_flag_only_push(hh);
+    }
+    if (rc) return rc;
+    return tail_run(hh, n, nullptr, /*from_peer=*/true);
+}
+
+int nufi_b200_peer_status(nufi_b200_handle *h, int *timed_out)
+{
+    PEER_ENTER(h);
+    if (!timed_out) return fail(hh, NUFI_B200_ERR_ARG, "timed_out is NULL");
+    *timed_out = 0;
+    if (!hh->px.d_status) return NUFI_B200_OK;
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    NUFI_CUDA_CHECK(hh, cudaMemcpy(timed_out, hh->px.d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    return NUFI_B200_OK;
+}
+
+} // extern "C"

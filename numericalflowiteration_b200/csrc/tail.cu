@@ -283,6 +283,7 @@ struct SmallTailParams
     const double2 *twx, *twy, *twz; // (cos, sin)(2 pi m / N_d)
     const double *rho;              // CPU-convention rho on the device, or nullptr: reduce the backtrace slots (F)
     FinishParams F;
+    PeerRecv X;                     // X.world > 0: rho = 1 + sum over ranks of the peer exchange buffer (waits for the flags)
     double *level, *raw1d, *energy_out;
 };
 
@@ -415,6 +416,14 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
     //      partial sums over the CTAs that touched its tile, then added in order -- the association of finish_rho_kernel)
     if (S.rho) {
         for (int l = threadIdx.x; l < N; l += blockDim.x) A[l] = make_double2(S.rho[l], 0.0);
+    } else if (S.X.world) { // multi-GPU step: the all-reduce happens here, over peer memory
+        peer_wait_all(S.X);
+        __syncthreads();
+        for (int l = threadIdx.x; l < N; l += blockDim.x) {
+            const double r = peer_sum(S.X, N, l);
+            S.X.rho_full[l] = r;
+            A[l] = make_double2(r, 0.0);
+        }
     } else {
         const FinishParams &F = S.F;
         auto slot_sum = [&](unsigned tile, unsigned lane, unsigned b_lo, unsigned b_hi, int w) {
@@ -659,7 +668,7 @@ static bool small_tail_ok(const Handle *h)
 
 // rho (CPU convention, device) -> level n in the device history + energy[n].
 // d_rho_full == nullptr: rho comes from the pending slot reduction of the last backtrace launch (fused step).
-int tail_run(Handle *h, size_t n, const double *d_rho_full)
+int tail_run(Handle *h, size_t n, const double *d_rho_full, bool from_peer)
 {
     const nufi_b200_config3d &c = h->c;
     TailParams T{};
@@ -688,7 +697,10 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full)
         S.level = level;
         S.raw1d = h->d_raw ? h->d_raw + n * h->raw_stride : nullptr;
         S.energy_out = h->d_energy + n;
-        if (d_rho_full) {
+        if (from_peer) {
+            S.rho = nullptr;
+            S.X = h->px.recv;
+        } else if (d_rho_full) {
             S.rho = d_rho_full;
         } else {
             if (!h->fin_pending) return fail(h, NUFI_B200_ERR_ARG, "field tail: no rho on the device");
@@ -707,6 +719,11 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full)
         return NUFI_B200_OK;
     }
 
+    if (from_peer) { // large grids: gather kernel (waits for the flags, sums in rank order) -> d_rho_full
+        int rc = launch_peer_gather(h);
+        if (rc) return rc;
+        d_rho_full = h->d_rho_full;
+    }
     if (!d_rho_full) { // the cuFFT path reads rho from memory: run the slot reduction first
         int rc = launch_finish(h);
         if (rc) return rc;

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["partition", "DistributedStepper"]
+__all__ = ["partition", "DistributedStepper", "attach_peers"]
 
 
 def partition(n_total: int, n_parts: int, part: int, begin: int = 0) -> tuple[int, int]:
@@ -29,7 +29,7 @@ class DistributedStepper:
     callable standing in for the device work, the reduction runs on host tensors.
     """
 
-    def __init__(self, sched, rank: int | None = None, world_size: int | None = None, group=None):
+    def __init__(self, sched, rank: int | None = None, world_size: int | None = None, group=None, exchange: str = "nccl"):
         import torch
         import torch.distributed as dist
 
@@ -44,6 +44,10 @@ class DistributedStepper:
             # run the library on torch's current stream so NCCL orders against it without host syncs
             sched.set_stream(torch.cuda.current_stream().cuda_stream)
             self._rho_t = _alias_device_f64(torch, sched.rho_device_ptr(), sched.n_nodes)
+        self.exchange = "nccl"
+        if exchange == "peer" and self.world > 1:
+            attach_peers(sched, self.rank, self.world, dist, group)
+            self.exchange = "peer-memory"
 
     def compute_rho(self, n: int):
         """Local partial rho of step n on the device (asynchronous)."""
@@ -56,10 +60,23 @@ class DistributedStepper:
         return self._rho_t
 
     def step(self, n: int) -> None:
-        """One time step: local backtrace -> all-reduce of rho -> replicated field tail -> level n."""
+        """One time step: local backtrace -> exchange of rho -> replicated field tail -> level n."""
+        if self.exchange == "peer-memory":
+            self.sched.peer_step(n)  # exchange fused into the kernels (stores into peer memory + flags)
+            return
         self.compute_rho(n)
         self.reduce_rho()
         self.sched.field_tail_device(n, self._rho_t.data_ptr())
+
+
+def attach_peers(sched, rank: int, world: int, dist, group=None) -> None:
+    """Maps every rank's exchange buffer into every other rank (CUDA IPC handles all-gathered through torch.distributed),
+    after which ``sched.peer_step(n)`` needs no collective call.  Raises CudaError if IPC mapping is not possible."""
+    mine = sched.peer_export(world)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine, group=group)
+    sched.peer_attach(rank, world, b"".join(gathered))
+    dist.barrier(group=group)  # everyone has mapped everyone before the first push
 
 
 class _CudaArray:

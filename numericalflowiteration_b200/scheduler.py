@@ -187,6 +187,32 @@ class CudaScheduler:
     def field_tail_device(self, n: int, d_rho_partial_sum: int) -> None:
         self._ck(self._L.nufi_b200_field_tail_device(self._h, n, C.c_void_p(d_rho_partial_sum)))
 
+    # -- multi-GPU step with the rho exchange fused into the kernels over NVLink peer memory (csrc/peer.cu)
+    PEER_HANDLE_BYTES = 64
+
+    def peer_export(self, world: int) -> bytes:
+        """Allocates this rank's exchange buffer; returns its CUDA IPC handle (all-gather these in rank order)."""
+        buf = C.create_string_buffer(self.PEER_HANDLE_BYTES)
+        self._ck(self._L.nufi_b200_peer_export(self._h, world, buf))
+        return buf.raw
+
+    def peer_attach(self, rank: int, world: int, handles: bytes) -> None:
+        """Maps the exchange buffers of all ranks (``handles`` = world x 64 bytes in rank order)."""
+        assert len(handles) == world * self.PEER_HANDLE_BYTES
+        self._ck(self._L.nufi_b200_peer_attach(self._h, rank, world, C.c_char_p(handles)))
+
+    def peer_step(self, n: int) -> None:
+        """Backtrace of this rank's q-share -> push into every GPU -> tail that waits for all ranks; asynchronous."""
+        self._ck(self._L.nufi_b200_peer_step(self._h, n))
+
+    def peer_timed_out(self) -> bool:
+        t = C.c_int(0)
+        self._ck(self._L.nufi_b200_peer_status(self._h, C.byref(t)))
+        return bool(t.value)
+
+    def peer_detach(self) -> None:
+        self._ck(self._L.nufi_b200_peer_detach(self._h))
+
     # -- introspection
     @property
     def launches(self) -> int:
@@ -241,9 +267,10 @@ def device_count() -> int:
 
 class CudaGroup:
     """Several GPUs driven by ONE process -- the shape of the reference's ``cuda_scheduler`` (one host thread, all visible
-    devices, nufi/cuda_scheduler.hpp:43-63) with the host fan-in replaced by an NCCL all-reduce on the devices.
-    ``step(n)``: every device traces its contiguous share of the flat q range, the partial rho vectors are summed in
-    place over NVLink, every device runs the (tiny, deterministic) field tail."""
+    devices, nufi/cuda_scheduler.hpp:43-63) with the host fan-in replaced by an exchange over NVLink on the devices.
+    ``step(n)``: every device traces its contiguous share of the flat q range, the partial rho vectors are exchanged
+    (stores into peer memory fused into the slot reduction, or an NCCL all-reduce), every device runs the (tiny,
+    deterministic) field tail."""
 
     def __init__(self, conf, f0: F0 | None = None, devices=None, order: int = 4):
         self._L = _lib.load()
@@ -258,6 +285,16 @@ class CudaGroup:
 
     def step(self, n: int) -> None:
         rc = self._L.nufi_b200_group_step(self._g, n)
+        if rc != _lib.OK:
+            _raise(rc, self._L.nufi_b200_group_last_error(self._g).decode())
+
+    @property
+    def exchange(self) -> str:
+        """'peer-memory' (fused into the kernels, default when the devices can map each other), 'nccl' or 'single'."""
+        return self._L.nufi_b200_group_exchange(self._g).decode()
+
+    def set_exchange(self, mode: str) -> None:
+        rc = self._L.nufi_b200_group_set_exchange(self._g, {"peer": 0, "peer-memory": 0, "nccl": 1}[mode])
         if rc != _lib.OK:
             _raise(rc, self._L.nufi_b200_group_last_error(self._g).decode())
 

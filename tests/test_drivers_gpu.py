@@ -104,3 +104,111 @@ def test_group_one_process_multi_gpu(oracle):
     for e, lv in zip(energies, levels):
         assert np.max(np.abs(e - want) / np.abs(want)) <= ENERGY_TOL
         assert np.array_equal(lv, levels[0])
+
+
+@pytest.mark.parametrize("case", ["1d-two-stream", "2d-landau", "3d-landau"])
+def test_peer_step_world1_matches_fused_step(case):
+    """The peer-memory exchange path with a world of one rank (push into the own buffer, flag, wait, rank-order sum) must
+    reproduce the plain fused step: same kernels as the multi-GPU path, runnable on a one-GPU box."""
+    mk, f0 = CASES[case]
+    conf = mk()
+    with CudaScheduler(conf, f0, device=0) as a, CudaScheduler(conf, f0, device=0) as b:
+        h = b.peer_export(1)
+        b.peer_attach(0, 1, h)
+        for n in range(conf.Nt):
+            a.step(n)
+            b.peer_step(n)
+        ea, eb = a.download_energy(0, conf.Nt), b.download_energy(0, conf.Nt)
+        assert not b.peer_timed_out()
+        assert np.max(np.abs(ea - eb) / np.abs(ea)) <= 1e-12
+        assert rel_linf(b.download_phi(conf.Nt - 1), a.download_phi(conf.Nt - 1)) <= 1e-12
+        assert rel_linf(b.eval_rho(conf.Nt - 1), a.eval_rho(conf.Nt - 1)) <= 1e-12
+        b.peer_detach()
+
+
+def test_peer_step_large_grid_uses_gather_kernel():
+    """Grids beyond the single-CTA tail take the peer_gather_kernel + cuFFT route."""
+    conf = Config2D(Nx=80, Ny=64, Nu=8, Nv=8, Nt=4)
+    f0 = F0(0, 0.05, 0.5)
+    with CudaScheduler(conf, f0, device=0) as a, CudaScheduler(conf, f0, device=0) as b:
+        b.peer_attach(0, 1, b.peer_export(1))
+        for n in range(conf.Nt):
+            a.step(n)
+            b.peer_step(n)
+        assert b.last_tail_variant == "cufft"
+        assert not b.peer_timed_out()
+        assert rel_linf(b.download_phi(conf.Nt - 1), a.download_phi(conf.Nt - 1)) <= 1e-12
+
+
+def test_peer_step_requires_attach():
+    mk, f0 = CASES["1d-landau"]
+    with CudaScheduler(mk(), f0, device=0) as s:
+        with pytest.raises(ValueError):
+            s.peer_step(0)
+
+
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_group_exchange_modes(oracle, mode):
+    """Both exchanges of the one-process group (stores into peer memory fused into the kernels / NCCL all-reduce) give
+    bit-identical replicas and the reference's energy trace.  Needs >= 2 GPUs."""
+    ndev = device_count()
+    if ndev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    mk, f0 = CASES["3d-landau"]
+    conf = mk()
+    _, want, _ = oracle.run(conf, f0, conf.Nt)
+    with CudaGroup(conf, f0, devices=range(ndev)) as g:
+        g.set_exchange(mode)
+        assert g.exchange == ("peer-memory" if mode == "peer" else "nccl")
+        for n in range(conf.Nt):
+            g.step(n)
+        g.sync()
+        energies = [s.download_energy(0, conf.Nt) for s in g.scheds]
+        levels = [s.download_phi(conf.Nt - 1) for s in g.scheds]
+        if mode == "peer":
+            assert not any(s.peer_timed_out() for s in g.scheds)
+    for e, lv in zip(energies, levels):
+        assert np.max(np.abs(e - want) / np.abs(want)) <= ENERGY_TOL
+        assert np.array_equal(lv, levels[0])
+
+
+def test_torchrun_peer_exchange_ipc(tmp_path):
+    """One process per GPU (torchrun): CUDA IPC handles all-gathered through torch.distributed, then peer_step with no
+    collective call; every rank's history must be bit-identical to rank 0's and match the NCCL all-reduce path.  >= 2 GPUs."""
+    ndev = device_count()
+    if ndev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    script = tmp_path / "peer_ranks.py"
+    script.write_text(
+        "import os, sys, numpy as np, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
+        "from cases import CASES\n"
+        "from numericalflowiteration_b200 import CudaScheduler\n"
+        "from numericalflowiteration_b200.distributed import DistributedStepper\n"
+        "rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])\n"
+        "torch.cuda.set_device(local)\n"
+        "dist.init_process_group('nccl', device_id=torch.device('cuda', local))\n"
+        "mk, f0 = CASES['2d-two-stream']\n"
+        "conf = mk()\n"
+        "out = {}\n"
+        "for mode in ('peer', 'nccl'):\n"
+        "    s = CudaScheduler(conf, f0, device=local)\n"
+        "    st = DistributedStepper(s, exchange=mode)\n"
+        "    for n in range(conf.Nt):\n"
+        "        st.step(n)\n"
+        "    s.sync()\n"
+        "    out[mode] = (s.download_energy(0, conf.Nt), s.download_phi(conf.Nt - 1))\n"
+        "    if mode == 'peer':\n"
+        "        assert st.exchange == 'peer-memory' and not s.peer_timed_out()\n"
+        "    dist.barrier()\n"
+        "    s.close()\n"
+        "lv = torch.from_numpy(out['peer'][1]).cuda()\n"
+        "ref = lv.clone(); dist.broadcast(ref, 0)\n"
+        "assert torch.equal(lv, ref), 'replicas differ'\n"
+        "assert np.max(np.abs(out['peer'][0] - out['nccl'][0]) / np.abs(out['nccl'][0])) <= 1e-10\n"
+        "dist.barrier(); dist.destroy_process_group()\n"
+        "print('rank', rank, 'ok')\n")
+    r = subprocess.run(["python", "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29571", str(script)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
