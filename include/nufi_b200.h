@@ -174,8 +174,10 @@ int nufi_b200_field_tail_device(nufi_b200_handle *h, size_t n, const double *d_r
  *      (replaces cuda_kernel::download_rho + host add, nufi/cuda_kernel.cu:135-145, nufi/cuda_scheduler.hpp:113-118, and the
  *      MPI_Allreduce of bin/test_nufi_gpu_3d.cpp:158).  One process per GPU: every rank calls peer_export (allocates its exchange
  *      buffer, returns a 64-byte CUDA IPC handle), the host layer all-gathers the handles (rank order), every rank calls
- *      peer_attach.  peer_step(n) = backtrace of this rank's share of the flat q range (the reference's split,
- *      nufi/cuda_scheduler.hpp:88-111) -> slot reduction that STORES the partial rho into every GPU's buffer and releases a
+ *      peer_attach.  peer_step(n) = backtrace of this rank's share of the quadrature points -- velocity nodes rank, rank+world,
+ *      ... of every spatial node, so all GPUs trace statistically identical samples of phase space (the reference's contiguous
+ *      flat-q split, nufi/cuda_scheduler.hpp:88-111, stays available through compute_rho(q_begin, q_end)) -> slot reduction
+ *      that STORES the partial rho into every GPU's buffer and releases a
  *      flag there -> field tail that acquires all ranks' flags and adds the contributions in rank order (bit-identical on all
  *      GPUs) -> level n.  Asynchronous, no collective call, no host synchronisation.  All ranks must call peer_step the same
  *      number of times; synchronise all ranks (host barrier) before peer_detach / destroy.  peer_status: blocking; *timed_out
@@ -211,7 +213,11 @@ int nufi_b200_device_count(int *count);
 int nufi_b200_device_of(const nufi_b200_handle *h);
 /* number of kernels this library launched on h since creation */
 uint64_t nufi_b200_launch_count(const nufi_b200_handle *h);
-/* GPU time in ms of the most recent backtrace kernel (CUDA events on the launching stream); blocking */
+/* on != 0: bracket every backtrace launch with a CUDA event pair on its stream (read back lazily by the two calls below).
+ * Off by default: an event between the backtrace kernel and the field tail would keep the tail from being launched
+ * programmatically behind it (griddepcontrol), which hides its launch latency. */
+int nufi_b200_set_kernel_timing(nufi_b200_handle *h, int on);
+/* GPU time in ms of the most recent timed backtrace kernel; blocking */
 int nufi_b200_last_backtrace_ms(nufi_b200_handle *h, float *ms);
 /* accumulated GPU time and number of backtrace kernel launches since the last reset (every launch is bracketed by a
  * CUDA event pair on its stream; the pairs are read back lazily, so this call blocks, the launches do not) */

@@ -70,6 +70,8 @@ void free_all(Handle *h)
     cudaFree(h->d_rho_partial); cudaFree(h->d_rho_full); cudaFree(h->d_partials);
     cudaFree(h->d_metrics); cudaFree(h->d_mpartials); cudaFree(h->d_energy); cudaFree(h->d_stage);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->h_up) cudaFreeHost(h->h_up);
+    if (h->ev_up) cudaEventDestroy(h->ev_up);
     for (cudaEvent_t e : h->ev_ring)
         if (e) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -147,6 +149,7 @@ int create_common(const nufi_b200_config3d &c, int dim, int order, const nufi_b2
     CREATE_CHECK(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
+    if (const char *e = std::getenv("NUFI_B200_PDL")) h->pdl = std::atoi(e) != 0;
     CREATE_CHECK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
     const size_t hist_bytes = (c.Nt + 1) * h->level_stride * sizeof(double);
@@ -169,6 +172,8 @@ int create_common(const nufi_b200_config3d &c, int dim, int order, const nufi_b2
     h->h_pinned_cap = h->stride_t > h->n_nodes ? h->stride_t : h->n_nodes;
     if (h->h_pinned_cap < c.Nt + 1) h->h_pinned_cap = c.Nt + 1;
     CREATE_CHECK(cudaMallocHost(&h->h_pinned, h->h_pinned_cap * sizeof(double)));
+    CREATE_CHECK(cudaMallocHost(&h->h_up, h->h_pinned_cap * sizeof(double)));
+    CREATE_CHECK(cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming));
 #undef CREATE_CHECK
     int rc = tail_init(h);
     if (rc != NUFI_B200_OK) {
@@ -183,6 +188,20 @@ int create_common(const nufi_b200_config3d &c, int dim, int order, const nufi_b2
 
 inline Handle *H(nufi_b200_handle *h) { return reinterpret_cast<Handle *>(h); }
 inline const Handle *H(const nufi_b200_handle *h) { return reinterpret_cast<const Handle *>(h); }
+
+// host -> device through the upload staging buffer: the caller's buffer is consumed on return, the stream is not synchronised
+int stage_upload(Handle *h, double *d_dst, const double *host_src, size_t count)
+{
+    if (h->ev_up_pending) {
+        NUFI_CUDA_CHECK(h, cudaEventSynchronize(h->ev_up)); // the previous copy out of h_up (normally long finished)
+        h->ev_up_pending = false;
+    }
+    std::memcpy(h->h_up, host_src, sizeof(double) * count);
+    NUFI_CUDA_CHECK(h, cudaMemcpyAsync(d_dst, h->h_up, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream));
+    NUFI_CUDA_CHECK(h, cudaEventRecord(h->ev_up, h->stream));
+    h->ev_up_pending = true;
+    return NUFI_B200_OK;
+}
 
 int check_levels(Handle *h, size_t first_needed_exclusive_end, const char *what)
 {
@@ -271,11 +290,12 @@ int nufi_b200_upload_phi(nufi_b200_handle *h, size_t n, const double *coeffs_bas
     ENTER(h);
     if (n > hh->Nt) return fail(hh, NUFI_B200_ERR_RANGE, "Time-step out of range.");
     if (!coeffs_base) return fail(hh, NUFI_B200_ERR_ARG, "coeffs is NULL");
-    std::memcpy(hh->h_pinned, coeffs_base + n * hh->stride_t, sizeof(double) * hh->stride_t); // slice n (cuda_kernel.cu:154-155)
-    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(hh->d_stage, hh->h_pinned, sizeof(double) * hh->stride_t, cudaMemcpyHostToDevice, hh->stream));
-    int rc = convert_level_to_device(hh, n, hh->d_stage);
+    // slice n (cuda_kernel.cu:154-155).  The reference's cudaMemcpy blocks; here the slice is staged in pinned memory, so the
+    // caller may reuse its array on return while copy and layout conversion run asynchronously on the stream.
+    int rc = stage_upload(hh, hh->d_stage, coeffs_base + n * hh->stride_t, hh->stride_t);
     if (rc) return rc;
-    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream)); // blocking, like cudaMemcpy in the reference
+    rc = convert_level_to_device(hh, n, hh->d_stage);
+    if (rc) return rc;
     hh->level_valid[n] = 1;
     return NUFI_B200_OK;
 }
@@ -339,11 +359,10 @@ int nufi_b200_solve_interpolate_host(nufi_b200_handle *h, size_t n, const double
 {
     ENTER(h);
     if (!rho_host) return fail(hh, NUFI_B200_ERR_ARG, "rho_host is NULL");
-    std::memcpy(hh->h_pinned, rho_host, sizeof(double) * hh->n_nodes);
-    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(hh->d_rho_full, hh->h_pinned, sizeof(double) * hh->n_nodes, cudaMemcpyHostToDevice, hh->stream));
-    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream)); // h_pinned is reused below
+    int rc = stage_upload(hh, hh->d_rho_full, rho_host, hh->n_nodes);
+    if (rc) return rc;
     double e = 0;
-    int rc = nufi_b200_solve_interpolate(h, n, &e);
+    rc = nufi_b200_solve_interpolate(h, n, energy ? &e : nullptr);
     if (rc) return rc;
     if (energy) *energy = e;
     return NUFI_B200_OK;
@@ -537,13 +556,23 @@ int nufi_b200_field_tail_device(nufi_b200_handle *h, size_t n, const double *d_r
 
 uint64_t nufi_b200_launch_count(const nufi_b200_handle *h) { return h ? H(h)->launches : 0; }
 
+int nufi_b200_set_kernel_timing(nufi_b200_handle *h, int on)
+{
+    ENTER(h);
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    int rc = ev_drain(hh);
+    if (rc) return rc;
+    hh->kernel_timing = on != 0;
+    return NUFI_B200_OK;
+}
+
 int nufi_b200_last_backtrace_ms(nufi_b200_handle *h, float *ms)
 {
     ENTER(h);
     if (!ms) return fail(hh, NUFI_B200_ERR_ARG, "ms is NULL");
     int rc = ev_drain(hh);
     if (rc) return rc;
-    if (hh->bt_count == 0) return fail(hh, NUFI_B200_ERR_RANGE, "no backtrace kernel has been launched yet");
+    if (hh->bt_count == 0) return fail(hh, NUFI_B200_ERR_RANGE, "no timed backtrace launch yet (enable nufi_b200_set_kernel_timing first)");
     *ms = static_cast<float>(hh->bt_ms_last);
     return NUFI_B200_OK;
 }

@@ -386,6 +386,7 @@ template <int DIM, int ILP, bool XPP> struct Tune
 template <int DIM, int ILP, bool STAGED, bool POW2, bool XPP>
 __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1) backtrace_kernel(const __grid_constant__ BtParams P)
 {
+    pdl_trigger(); // the slot reduction / field tail behind this launch may be scheduled as soon as an SM has room
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);
     unsigned long long *empty = full + kMaxStages;
@@ -498,10 +499,11 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1) backtrace
         for (int i = 0; i < ILP; ++i) {
             unsigned long long j = P.interleave ? static_cast<unsigned long long>(jc) + static_cast<unsigned long long>(i) * P.upt
                                                 : static_cast<unsigned long long>(jc) * ILP + i;
-            ok[i] = node_ok && j < P.Nvel;
+            ok[i] = node_ok && j < P.Nvel_loc;
+            if (j >= P.Nvel_loc) j = 0;
+            j = j * P.vstride + P.voff; // this GPU's share of the velocity nodes (multi-GPU step: every vstride-th one)
             const unsigned long long q = l * P.Nvel + j;
             ok[i] = ok[i] && q >= P.q_begin && q < P.q_end;
-            if (j >= P.Nvel) j = 0;
             const int iu = static_cast<int>(j % P.Nu);
             const int iv = DIM >= 2 ? static_cast<int>((j / P.Nu) % P.Nv) : 0;
             const int iw = DIM >= 3 ? static_cast<int>(j / (static_cast<unsigned long long>(P.Nu) * P.Nv)) : 0;
@@ -620,6 +622,8 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1) backtrace
 __global__ void __launch_bounds__(256) finish_rho_kernel(const __grid_constant__ FinishParams F)
 {
     __shared__ double part[8][32];
+    pdl_wait();
+    pdl_trigger();
     const unsigned tile = blockIdx.x;
     const int lane = threadIdx.x & 31;
     const unsigned wj = threadIdx.x >> 5;
@@ -656,6 +660,8 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 __global__ void __launch_bounds__(256) finish_push_kernel(const __grid_constant__ FinishParams F, const __grid_constant__ PeerPush X)
 {
     __shared__ double part[8][32];
+    pdl_wait();
+    pdl_trigger();
     const unsigned tile = blockIdx.x;
     const int lane = threadIdx.x & 31;
     const unsigned wj = threadIdx.x >> 5;
@@ -887,6 +893,10 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     P.mweight = h->dim == 1 ? c.du * c.dx : (h->dim == 2 ? c.dx * c.dy * c.du * c.dv : c.du * c.dv * c.dw);
 
     P.Nvel = h->n_vel;
+    P.vstride = h->vstride > 0 ? h->vstride : 1;
+    P.voff = h->voff;
+    P.Nvel_loc = P.voff < P.Nvel ? (P.Nvel - P.voff + P.vstride - 1) / P.vstride : 0;
+    if (P.Nvel_loc == 0) return fail(h, NUFI_B200_ERR_ARG, "velocity share of this GPU is empty");
     P.q_begin = q_begin; P.q_end = q_end;
     P.l_first = q_begin / P.Nvel;
     P.l_last = (q_end - 1) / P.Nvel;
@@ -929,7 +939,7 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
             // 3d: one point per thread at 128 registers (16 warps) beats two points at 255 (8 warps) -- measured
             if (!force_ilp && h->dim == 3 && ilp == 2) continue;
             const unsigned wmax = max_threads_for(h->dim, ilp, h->xpp) / 32 - (staged ? 1 : 0);
-            const unsigned long long upt = (P.Nvel + ilp - 1) / ilp;
+            const unsigned long long upt = (P.Nvel_loc + ilp - 1) / ilp;
             for (unsigned W = 1; W <= wmax; ++W) {
                 if (force_w && static_cast<int>(W) != force_w) continue;
                 const unsigned long long rpt = (upt + W - 1) / W;
@@ -948,7 +958,7 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     }
     const int ilp = best_ilp;
     P.W = best_W;
-    P.upt = static_cast<unsigned>((P.Nvel + ilp - 1) / ilp);
+    P.upt = static_cast<unsigned>((P.Nvel_loc + ilp - 1) / ilp);
     P.rpt = (P.upt + P.W - 1) / P.W;
     const unsigned long long R64 = static_cast<unsigned long long>(P.rpt) * P.n_tiles;
     if (R64 >= (1ull << 31)) return fail(h, NUFI_B200_ERR_RANGE, "quadrature range too large for one launch");
@@ -976,19 +986,21 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
         NUFI_CUDA_CHECK(h, cudaMemsetAsync(h->d_mpartials, 0, sizeof(double) * 4 * grid, h->stream));
     }
 
-    cudaEvent_t ev_start, ev_stop;
-    {
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    if (h->kernel_timing) { // off by default: an event between two kernels keeps the second from launching programmatically
         int rc = ev_acquire(h, &ev_start, &ev_stop);
         if (rc) return rc;
+        NUFI_CUDA_CHECK(h, cudaEventRecord(ev_start, h->stream));
     }
-    NUFI_CUDA_CHECK(h, cudaEventRecord(ev_start, h->stream));
     cudaError_t e;
     if (h->dim == 1) e = launch_dim<1>(P, ilp, false, staged, pow2, grid, threads, smem_bytes, h->stream);
     else if (h->dim == 2) e = launch_dim<2>(P, ilp, h->xpp, staged, pow2, grid, threads, smem_bytes, h->stream);
     else e = launch_dim<3>(P, ilp, h->xpp, staged, pow2, grid, threads, smem_bytes, h->stream);
     NUFI_CUDA_CHECK(h, e);
-    NUFI_CUDA_CHECK(h, cudaEventRecord(ev_stop, h->stream));
-    h->ev_pending += 1;
+    if (h->kernel_timing) {
+        NUFI_CUDA_CHECK(h, cudaEventRecord(ev_stop, h->stream));
+        h->ev_pending += 1;
+    }
     h->launches += 1;
     const char *fmt = h->xpp ? "/xpp" : "";
     if (staged) std::snprintf(h->variant_buf, sizeof(h->variant_buf), "smem-tma%s/ilp%d/W%u/Lc%dx%d", fmt, ilp, P.W, P.Lc, P.stages);
@@ -999,13 +1011,14 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
         FinishParams F{};
         F.slots = h->d_partials;
         F.rho_partial = h->d_rho_partial;
-        const bool whole = q_begin == 0 && q_end == h->n_nodes * h->n_vel;
+        const bool all_nodes = q_begin == 0 && q_end == h->n_nodes * h->n_vel; // every node's value gets written
+        const bool whole = all_nodes && P.vstride == 1;                         // ... and it is the complete sum
         F.rho_full = whole ? h->d_rho_full : nullptr;
         F.dV = h->dim == 1 ? P.du : (h->dim == 2 ? P.du * P.dv : P.du * P.dv * P.dw); // rho.hpp:145, 307, 459
         F.l_first = P.l_first; F.l_last = P.l_last;
         F.rpt = P.rpt; F.rpc = P.rpc; F.Tmax = P.Tmax;
         F.n_tiles = P.n_tiles;
-        if (!whole) NUFI_CUDA_CHECK(h, cudaMemsetAsync(h->d_rho_partial, 0, sizeof(double) * h->n_nodes, h->stream));
+        if (!all_nodes) NUFI_CUDA_CHECK(h, cudaMemsetAsync(h->d_rho_partial, 0, sizeof(double) * h->n_nodes, h->stream));
         h->fin = F;
         h->fin_pending = true;
         if (!(defer_finish && whole)) return launch_finish(h);
@@ -1085,8 +1098,8 @@ int launch_flag_only_push(Handle *h)
 int launch_finish(Handle *h)
 {
     if (!h->fin_pending) return NUFI_B200_OK;
-    if (h->fin_push) finish_push_kernel<<<h->fin.n_tiles ? h->fin.n_tiles : 1, 256, 0, h->stream>>>(h->fin, h->px.push);
-    else finish_rho_kernel<<<h->fin.n_tiles, 256, 0, h->stream>>>(h->fin);
+    if (h->fin_push) NUFI_CUDA_CHECK(h, launch_chained(h, finish_push_kernel, dim3(h->fin.n_tiles ? h->fin.n_tiles : 1), dim3(256), 0, h->fin, h->px.push));
+    else NUFI_CUDA_CHECK(h, launch_chained(h, finish_rho_kernel, dim3(h->fin.n_tiles), dim3(256), 0, h->fin));
     h->fin_push = false;
     NUFI_CUDA_CHECK(h, cudaGetLastError());
     h->fin_pending = false;

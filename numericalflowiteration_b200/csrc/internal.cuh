@@ -35,6 +35,7 @@ struct BtParams
     double f0p[4];
     // work decomposition (see backtrace.cu)
     unsigned long long q_begin, q_end, Nvel;
+    unsigned long long Nvel_loc, vstride, voff; // this launch traces velocity nodes voff, voff+vstride, ... (Nvel_loc of them)
     unsigned long long l_first;      // first spatial node touched by [q_begin,q_end)
     unsigned long long l_last;       // last spatial node touched
     unsigned int n_tiles;            // tiles of 32 consecutive nodes
@@ -94,6 +95,13 @@ struct PeerRecv // receiver side (tail_small_kernel / peer_gather_kernel)
 };
 
 #ifdef __CUDACC__
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor still runs; it must execute pdl_wait() before touching anything the predecessor writes (the wait
+// returns once the predecessor grid has completed and its memory is visible).  pdl_trigger() in the predecessor lets the
+// dependent grid be scheduled as soon as SM resources allow.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Receiver: thread r < world spins (bounded, ~2 s) until rank r's flag of this epoch has arrived.  Call from all threads
 // of the block and follow with __syncthreads(); read the data with __ldcg (L2: the peers wrote it behind L1's back).
 __device__ __forceinline__ void peer_wait_all(const PeerRecv &X)
@@ -159,6 +167,9 @@ struct Handle
     double *d_stage = nullptr;  // device staging for one reference-format level
     double *h_pinned = nullptr; // pinned host staging (max(stride_t, n_nodes) doubles)
     size_t h_pinned_cap = 0;
+    double *h_up = nullptr;     // second pinned staging buffer, host -> device only: uploads return without a stream sync
+    cudaEvent_t ev_up = nullptr; // recorded behind the last copy out of h_up; waited for before h_up is overwritten
+    bool ev_up_pending = false;
     // tail
     cufftHandle plan_fwd = 0, plan_inv = 0;
     bool plans = false;
@@ -179,8 +190,11 @@ struct Handle
     size_t ev_head = 0, ev_pending = 0; // next slot (in pairs), pairs recorded but not yet read
     double bt_ms_total = 0, bt_ms_last = 0;
     uint64_t bt_count = 0;
+    bool kernel_timing = false;  // bracket every backtrace launch with a CUDA event pair (nufi_b200_set_kernel_timing)
+    bool pdl = true;             // programmatic dependent launch of finish / tail behind the backtrace kernel (NUFI_B200_PDL=0: off)
     int sm_count = 148;
     size_t smem_optin = 0;
+    unsigned long long vstride = 1, voff = 0; // velocity share of the next backtrace launch (multi-GPU step), else 1, 0
     PeerState px;
     bool fin_push = false;       // the pending slot reduction also pushes to the peers (finish_push_kernel)
     int variant_force = 0;
@@ -189,6 +203,24 @@ struct Handle
     uint64_t launches = 0;
     std::string err;
 };
+
+// Launch `kern` on h->stream as a programmatic dependent of whatever precedes it there (safe after any predecessor: the
+// kernel itself calls pdl_wait() before it reads or writes anything a predecessor touches).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chained(Handle *h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // error helpers (api.cu)
 int fail(Handle *h, int code, const std::string &msg);

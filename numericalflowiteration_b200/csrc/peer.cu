@@ -24,6 +24,7 @@ namespace
 // exchange buffer -> d_rho_full for grids too large for the single-CTA tail (the cuFFT path reads rho from memory)
 __global__ void __launch_bounds__(256) peer_gather_kernel(const __grid_constant__ PeerRecv X, size_t n_nodes)
 {
+    pdl_wait();
     peer_wait_all(X);
     __syncthreads();
     for (size_t l = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; l < n_nodes; l += static_cast<size_t>(gridDim.x) * blockDim.x)
@@ -66,8 +67,7 @@ int peer_alloc(Handle *h, int world)
     return NUFI_B200_OK;
 }
 
-// Next epoch: pointers for the sender, ranges for the receiver.  The q-range split is the reference scheduler's
-// (nufi/cuda_scheduler.hpp:88-111): contiguous, the first Nquad % world shares one longer.
+// Next epoch: pointers for the sender, node ranges for the receiver.
 int peer_prepare_step(Handle *h)
 {
     PeerState &px = h->px;
@@ -89,13 +89,9 @@ int peer_prepare_step(Handle *h)
     R.data = reinterpret_cast<const double *>(px.xb + data_offset(h, parity, 0));
     R.rho_full = h->d_rho_full;
     R.status = px.d_status;
-    const size_t nq = h->n_nodes * h->n_vel, chunk = nq / px.world, rem = nq % px.world;
-    size_t q0 = 0;
-    for (int r = 0; r < px.world; ++r) {
-        const size_t q1 = q0 + chunk + (static_cast<size_t>(r) < rem ? 1 : 0);
-        if (q1 > q0) { R.l_first[r] = q0 / h->n_vel; R.l_last[r] = (q1 - 1) / h->n_vel; }
+    for (int r = 0; r < px.world; ++r) { // rank r traces velocity nodes r, r+world, ... of EVERY spatial node (see peer_step)
+        if (static_cast<size_t>(r) < h->n_vel) { R.l_first[r] = 0; R.l_last[r] = h->n_nodes - 1; }
         else { R.l_first[r] = 1; R.l_last[r] = 0; }
-        q0 = q1;
     }
     px.push = P;
     px.recv = R;
@@ -106,8 +102,7 @@ int launch_peer_gather(Handle *h)
 {
     size_t blocks = (h->n_nodes + 255) / 256;
     if (blocks > 592) blocks = 592;
-    peer_gather_kernel<<<static_cast<unsigned>(blocks), 256, 0, h->stream>>>(h->px.recv, h->n_nodes);
-    NUFI_CUDA_CHECK(h, cudaGetLastError());
+    NUFI_CUDA_CHECK(h, launch_chained(h, peer_gather_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, h->px.recv, h->n_nodes));
     h->launches += 1;
     return NUFI_B200_OK;
 }
@@ -183,13 +178,18 @@ int nufi_b200_peer_step(nufi_b200_handle *h, size_t n)
     int rc = peer_prepare_step(hh);
     if (rc) return rc;
     const PeerState &px = hh->px;
-    const size_t nq = hh->n_nodes * hh->n_vel, chunk = nq / px.world, rem = nq % px.world;
-    const size_t r = static_cast<size_t>(px.rank);
-    const size_t q0 = r * chunk + (r < rem ? r : rem), q1 = q0 + chunk + (r < rem ? 1 : 0);
-    if (q1 > q0) {
+    // Sharding of the fused multi-GPU step: rank r takes the velocity nodes r, r+world, r+2 world, ... of every spatial node.
+    // (compute_rho keeps the reference's contiguous flat-q split, nufi/cuda_scheduler.hpp:88-111; that split hands each GPU
+    // a different region of phase space, and regions differ in cost -- trapped orbits replay shared-memory loads -- so the
+    // step would wait for the slowest GPU.  The interleaved split gives every GPU a statistically identical sample.)
+    if (static_cast<size_t>(px.rank) < hh->n_vel) {
         hh->fin_push = true;
-        rc = nufi_b200_compute_rho(h, n, q0, q1); // backtrace, then finish_push_kernel instead of finish_rho_kernel
+        hh->vstride = static_cast<unsigned long long>(px.world);
+        hh->voff = static_cast<unsigned long long>(px.rank);
+        rc = nufi_b200_compute_rho(h, n, 0, hh->n_nodes * hh->n_vel); // backtrace, then finish_push_kernel (not finish_rho_kernel)
         hh->fin_push = false;
+        hh->vstride = 1;
+        hh->voff = 0;
     } else {
         rc = launch_flag_only_push(hh);
     }

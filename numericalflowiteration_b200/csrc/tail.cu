@@ -412,6 +412,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
         ilx[i] = T.ilx[i];
         kap2x[i] = T.kap2x[i];
     }
+    pdl_wait(); // everything below reads what the kernels ahead of this one on the stream wrote
     // ---- rho (either given, or the fixed-order sum of the backtrace kernel's per-(CTA, tile) slots: per node 8 strided
     //      partial sums over the CTAs that touched its tile, then added in order -- the association of finish_rho_kernel)
     if (S.rho) {
@@ -711,8 +712,7 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full, bool from_peer)
         const size_t smem = (2 * h->n_nodes + 2 * (c.Nx + c.Ny + c.Nz) + kSmallPart) * sizeof(double2) + ((c.Nx + c.Ny + c.Nz + 1) & ~size_t(1)) * sizeof(double);
         if (smem > 48 * 1024)
             NUFI_CUDA_CHECK(h, cudaFuncSetAttribute(tail_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        tail_small_kernel<<<1, kSmallThreads, smem, h->stream>>>(S);
-        NUFI_CUDA_CHECK(h, cudaGetLastError());
+        NUFI_CUDA_CHECK(h, launch_chained(h, tail_small_kernel, dim3(1), dim3(kSmallThreads), smem, S));
         h->launches += 1;
         h->last_tail = "fused-1cta";
         h->level_valid[n] = 1;

@@ -40,9 +40,13 @@ class DistributedStepper:
         self.world = dist.get_world_size(group) if world_size is None else world_size
         self.q_begin, self.q_end = partition(sched.n_quad, self.world, self.rank)
         self._rho_t = None
+        self._stream = None
         if torch.cuda.is_available() and hasattr(sched, "rho_device_ptr"):
-            # run the library on torch's current stream so NCCL orders against it without host syncs
-            sched.set_stream(torch.cuda.current_stream().cuda_stream)
+            # the library and the NCCL all-reduce share ONE explicit torch stream, so the collective is ordered after the
+            # backtrace and before the tail without host syncs (torch's legacy default stream would map to the handle's own
+            # non-blocking stream, which NCCL does not order against)
+            self._stream = torch.cuda.Stream()
+            sched.set_stream(self._stream.cuda_stream)
             self._rho_t = _alias_device_f64(torch, sched.rho_device_ptr(), sched.n_nodes)
         self.exchange = "nccl"
         if exchange == "peer" and self.world > 1:
@@ -56,7 +60,11 @@ class DistributedStepper:
     def reduce_rho(self):
         """Sum of the partial rho vectors over all ranks, in place on the device."""
         if self.world > 1:
-            self.dist.all_reduce(self._rho_t, op=self.dist.ReduceOp.SUM, group=self.group)
+            if self._stream is not None:
+                with self.torch.cuda.stream(self._stream):
+                    self.dist.all_reduce(self._rho_t, op=self.dist.ReduceOp.SUM, group=self.group)
+            else:
+                self.dist.all_reduce(self._rho_t, op=self.dist.ReduceOp.SUM, group=self.group)
         return self._rho_t
 
     def step(self, n: int) -> None:

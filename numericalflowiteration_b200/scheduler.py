@@ -218,6 +218,11 @@ class CudaScheduler:
     def launches(self) -> int:
         return int(self._L.nufi_b200_launch_count(self._h))
 
+    def set_kernel_timing(self, on: bool) -> None:
+        """Bracket every backtrace launch with a CUDA event pair (needed by last_backtrace_ms / backtrace_time; off by
+        default because the events keep the field tail from launching programmatically behind the kernel)."""
+        self._ck(self._L.nufi_b200_set_kernel_timing(self._h, int(on)))
+
     def last_backtrace_ms(self) -> float:
         ms = C.c_float(0)
         self._ck(self._L.nufi_b200_last_backtrace_ms(self._h, C.byref(ms)))

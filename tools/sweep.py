@@ -33,6 +33,7 @@ def main():
     torch.cuda.set_device(0)
     r = GpuRunner(conf, f0, 0, 1, torch, None)
     free_run(r, n)
+    r.s.set_kernel_timing(True)
     ps = float(n_quad(conf)) * n
     print(desc, "depth", n, flush=True)
     for ilp, W, lc in itertools.product(a.ilp, a.W, a.lc):
