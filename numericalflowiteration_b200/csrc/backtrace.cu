@@ -354,6 +354,25 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "r"(parity)
         : "memory");
 }
+// the same on precomputed 32-bit shared addresses (hot loop: no generic->shared conversion per use)
+__device__ __forceinline__ void mbar_arrive_a(unsigned bar)
+{
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
 {
@@ -401,7 +420,11 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1) backtrace
     if (g0 >= P.R) return; // whole CTA idle (uniform)
     const unsigned my_rounds = min(P.rpc, P.R - g0);
     const unsigned t_first = g0 / P.rpt;
-    const int c_hi = P.first_level >= 0 ? P.first_level / P.Lc : -1;
+    // Chunks of the history, newest first, aligned at the TOP: chunk i holds levels [first_level - (i+1) Lc + 1, first_level - i Lc],
+    // so every chunk but the last (which ends at level 0) has exactly Lc levels and the per-chunk code has no ragged cases.
+    const int n_levels = P.first_level + 1;
+    const int n_chunks = n_levels > 0 ? (n_levels + P.Lc - 1) / P.Lc : 0;
+    const int rem_levels = n_levels - (n_chunks - 1) * P.Lc; // levels in the bottom chunk, 1..Lc
     const unsigned level_doubles = P.level_bytes / 8;
 
     if constexpr (STAGED) {
@@ -422,13 +445,14 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1) backtrace
             unsigned ph = 0;
             bool primed = false;
             for (unsigned r = 0; r < my_rounds; ++r)
-                for (int c = c_hi; c >= 0; --c) {
+                for (int ci = 0; ci < n_chunks; ++ci) {
                     if (primed) mbar_wait(&empty[s], ph ^ 1u);
-                    const int lv_top = c == c_hi ? P.first_level - c * P.Lc : P.Lc - 1;
-                    const unsigned bytes = static_cast<unsigned>(lv_top + 1) * P.level_bytes;
+                    const bool bottom = ci == n_chunks - 1;
+                    const int cnt = bottom ? rem_levels : P.Lc;
+                    const int lv_lo = bottom ? 0 : P.first_level - (ci + 1) * P.Lc + 1;
+                    const unsigned bytes = static_cast<unsigned>(cnt) * P.level_bytes;
                     mbar_expect_tx(&full[s], bytes);
-                    const unsigned char *src =
-                        reinterpret_cast<const unsigned char *>(P.hist) + static_cast<size_t>(c) * P.Lc * P.level_bytes;
+                    const unsigned char *src = reinterpret_cast<const unsigned char *>(P.hist) + static_cast<size_t>(lv_lo) * P.level_bytes;
                     unsigned char *dst = const_cast<unsigned char *>(ring) + static_cast<size_t>(s) * P.stage_bytes;
                     for (unsigned off = 0; off < bytes; off += 32768u)
                         bulk_g2s(dst + off, src + off, min(32768u, bytes - off), &full[s]);
@@ -470,7 +494,7 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1) backtrace
         const unsigned jc = P.interleave ? jr + warp * P.rpt : jr * W + warp;
         if (jc >= P.upt) { // no unit for this warp in this round: keep the stage protocol going
             if constexpr (STAGED) {
-                for (int c = c_hi; c >= 0; --c) {
+                for (int ci = 0; ci < n_chunks; ++ci) {
                     mbar_wait(&full[s], ph);
                     if (lane == 0) mbar_arrive(&empty[s]);
                     if (++s == P.stages) { s = 0; ph ^= 1u; }
@@ -527,37 +551,47 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1) backtrace
         }
 
         // ---- the trace: chunks newest -> oldest; inside a chunk levels top -> bottom
-        for (int c = c_hi; c >= 0; --c) {
-            const double *base;
-            int j = c == c_hi ? P.first_level - c * P.Lc : P.Lc - 1;
-            if constexpr (STAGED) {
-                mbar_wait(&full[s], ph);
-                base = reinterpret_cast<const double *>(ring + static_cast<size_t>(s) * P.stage_bytes);
-            } else {
-                base = P.hist + static_cast<size_t>(c) * P.Lc * level_doubles;
-            }
-            const double *lev = base + static_cast<size_t>(j) * level_doubles;
-            if (P.metrics && c == c_hi) { // eval_f: half kick on level n at the starting position
+        {
+            const unsigned full0 = smem_u32(full), empty0 = smem_u32(empty);
+            const int Lc = P.Lc;
+            for (int ci = 0; ci < n_chunks; ++ci) {
+                const bool bottom = ci == n_chunks - 1;
+                int cnt = bottom ? rem_levels : Lc; // levels in this chunk
+                const double *base;
+                if constexpr (STAGED) {
+                    mbar_wait_a(full0 + 8u * s, ph);
+                    base = reinterpret_cast<const double *>(ring + static_cast<size_t>(s) * P.stage_bytes);
+                } else {
+                    base = P.hist + static_cast<size_t>(bottom ? 0 : P.first_level - (ci + 1) * Lc + 1) * level_doubles;
+                }
+                const double *lev = base + static_cast<size_t>(cnt - 1) * level_doubles;
+                if (P.metrics && ci == 0) { // eval_f: half kick on level n at the starting position
 #pragma unroll
-                for (int i = 0; i < ILP; ++i) step<DIM, FIRST, STAGED, POW2, XPP>(pt[i], lev, P, bad[i]);
-                --j;
-                lev -= level_doubles;
-            }
-            const int j_lo = c == 0 ? 1 : 0;
-#pragma unroll 2
-            for (; j >= j_lo; --j) {
+                    for (int i = 0; i < ILP; ++i) step<DIM, FIRST, STAGED, POW2, XPP>(pt[i], lev, P, bad[i]);
+                    --cnt;
+                    lev -= level_doubles;
+                }
+                if (bottom) --cnt; // level 0 takes the half kick below
+                for (int k = cnt >> 1; k > 0; --k) { // full-kick steps, two levels per trip
 #pragma unroll
-                for (int i = 0; i < ILP; ++i) step<DIM, FULL, STAGED, POW2, XPP>(pt[i], lev, P, bad[i]);
-                lev -= level_doubles;
-            }
-            if (c == 0 && j == 0) { // level 0: drift + half kick
+                    for (int i = 0; i < ILP; ++i) step<DIM, FULL, STAGED, POW2, XPP>(pt[i], lev, P, bad[i]);
 #pragma unroll
-                for (int i = 0; i < ILP; ++i) step<DIM, LAST, STAGED, POW2, XPP>(pt[i], base, P, bad[i]);
-            }
-            if constexpr (STAGED) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
-                if (++s == P.stages) { s = 0; ph ^= 1u; }
+                    for (int i = 0; i < ILP; ++i) step<DIM, FULL, STAGED, POW2, XPP>(pt[i], lev - level_doubles, P, bad[i]);
+                    lev -= 2 * level_doubles;
+                }
+                if (cnt & 1) {
+#pragma unroll
+                    for (int i = 0; i < ILP; ++i) step<DIM, FULL, STAGED, POW2, XPP>(pt[i], lev, P, bad[i]);
+                }
+                if (bottom) { // level 0: drift + half kick
+#pragma unroll
+                    for (int i = 0; i < ILP; ++i) step<DIM, LAST, STAGED, POW2, XPP>(pt[i], base, P, bad[i]);
+                }
+                if constexpr (STAGED) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_a(empty0 + 8u * s);
+                    if (++s == P.stages) { s = 0; ph ^= 1u; }
+                }
             }
         }
 
@@ -916,7 +950,9 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     // ---- chunking of the staged history
     P.Lc = 1; P.stages = 0; P.stage_bytes = P.level_bytes;
     if (staged) {
-        int Lc = static_cast<int>((32u * 1024u) / P.level_bytes);
+        // as many levels per chunk as a two-stage ring allows (cap 16): the per-chunk bookkeeping (barrier wait/arrive, pointer
+        // set-up) is paid once per Lc levels -- measured C1 0.117 -> 0.096 ms (Lc 5 -> 16), C3 8.65 -> 7.86 ms (Lc 1 -> 3)
+        int Lc = static_cast<int>(ring_budget / (2ull * P.level_bytes));
         Lc = env_int("NUFI_B200_LC", Lc);
         Lc = Lc < 1 ? 1 : (Lc > 16 ? 16 : Lc);
         while (Lc > 1 && 2ull * Lc * P.level_bytes > ring_budget) --Lc;
@@ -925,6 +961,8 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
         const int n_chunks = P.first_level / Lc + 1;
         if (stages > n_chunks) stages = n_chunks > 2 ? n_chunks : 2;
         P.Lc = Lc; P.stages = stages; P.stage_bytes = static_cast<unsigned>(Lc) * P.level_bytes;
+    } else if (P.first_level >= 0) {
+        P.Lc = P.first_level + 1; // global variant: the whole history is one "chunk" read in place
     }
 
     // ---- shape: points per thread (ILP) and consumer warps per CTA (W); a CTA-round = W warp-units of one tile

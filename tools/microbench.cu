@@ -1,0 +1,112 @@
+// Dependent-chain latencies on sm_100a of the FP64 / conversion / shared-memory instructions the 1d backtrace step is built
+// from (one warp, one CTA; cycles per dependent op from clock64).  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3
+//   -o tools/build/microbench tools/microbench.cu ; run on the GPU box.  Evidence for DESIGN.md's latency-chain analysis.
+#include <cstdio>
+#include <cuda_runtime.h>
+
+constexpr int N = 4096;
+
+template <int OP> __global__ void chain(double *out, double a, double b, long long *cycles)
+{
+    __shared__ double sm[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = 1e-9 * i;
+    __syncthreads();
+    double x = a + threadIdx.x * 1e-3;
+    int k = threadIdx.x;
+    const long long t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; ++i) {
+        if (OP == 0) x = fma(x, b, a);                          // DFMA
+        if (OP == 1) x = x + b;                                 // DADD
+        if (OP == 2) { double y = x + 6755399441055744.0; x = x - (y - 6755399441055744.0) + b; } // magic round: 3 DADD (+1)
+        if (OP == 3) x = x - rint(x) + b;                       // FRND + 2 DADD
+        if (OP == 4) { long long q = __double2ll_rn(x * 4503599627370496.0); x = static_cast<double>(q & 0xfffffffffffffll) * 2.220446049250313e-16 + b; } // F2I + I2F + mul/fma
+        if (OP == 5) { k = (k + __double2loint(x + 6755399441055744.0)) & 1023; x = x + sm[k]; } // DADD, IADD, LOP, LDS, DADD
+        if (OP == 6) { k = (k * 3 + 1) & 1023; k = k + __double2loint(sm[k]); }                 // LDS -> int chain
+        if (OP == 7) x = fma(x, fma(x, b, a), a);               // 2 DFMA (Horner)
+    }
+    const long long t1 = clock64();
+    out[threadIdx.x] = x + k;
+    if (threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+// Shared-memory load throughput of one SM: `warps` warps issue independent conflict-free loads of WIDTH bytes per lane
+// (STRIDE doubles between neighbouring lanes: 1 = dense, 3 = the 1d level layout [p0 p1 p2] per cell) back to back.
+template <int WIDTH, int STRIDE> __global__ void lds_tp(double *out, long long *cycles, int iters)
+{
+    extern __shared__ __align__(16) double smd[];
+    for (int i = threadIdx.x; i < 12288; i += blockDim.x) smd[i] = 1e-9 * i;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+    int base = (warp * 97) & 1023;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = ((base + u * 40) & 2047) + lane * STRIDE;
+            if (WIDTH == 4) {
+                acc0 += reinterpret_cast<const float *>(smd)[idx];
+            } else if (WIDTH == 8) {
+                acc0 += smd[idx];
+            } else {
+                const double2 v = *reinterpret_cast<const double2 *>(smd + 2 * (idx >> 1) + 0);
+                acc0 += v.x;
+                acc1 += v.y;
+            }
+        }
+        base += 8;
+    }
+    const long long t1 = clock64();
+    out[threadIdx.x] = acc0 + acc1 + acc2 + acc3;
+    if (threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+template <int WIDTH, int STRIDE> void run_tp(const char *name, double *d_out, long long *d_cyc, int warps)
+{
+    const int iters = 2000;
+    cudaFuncSetAttribute(lds_tp<WIDTH, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 8);
+    lds_tp<WIDTH, STRIDE><<<1, warps * 32, 12288 * 8>>>(d_out, d_cyc, iters);
+    lds_tp<WIDTH, STRIDE><<<1, warps * 32, 12288 * 8>>>(d_out, d_cyc, iters);
+    long long c = 0;
+    cudaMemcpy(&c, d_cyc, sizeof(c), cudaMemcpyDeviceToHost);
+    const double instr = double(iters) * 8 * warps;
+    printf("%-34s %2d warps: %6.2f cycles per warp-load, %6.1f B/clk/SM (includes the dependent FP64 adds)\n", name, warps, c / instr,
+           instr * 32 * WIDTH / c);
+}
+
+template <int OP> void run(const char *name, double *d_out, long long *d_cyc, double b, int ops)
+{
+    chain<OP><<<1, 32>>>(d_out, 0.3, b, d_cyc);
+    chain<OP><<<1, 32>>>(d_out, 0.3, b, d_cyc);
+    long long c = 0;
+    cudaMemcpy(&c, d_cyc, sizeof(c), cudaMemcpyDeviceToHost);
+    printf("%-44s %8.2f cycles per iteration  (%d dependent ops -> %.2f per op)\n", name, double(c) / N, ops, double(c) / N / ops);
+}
+
+int main()
+{
+    double *d_out;
+    long long *d_cyc;
+    cudaMalloc(&d_out, 32 * sizeof(double));
+    cudaMalloc(&d_cyc, sizeof(long long));
+    run<0>("DFMA chain", d_out, d_cyc, 0.999, 1);
+    run<1>("DADD chain", d_out, d_cyc, 1e-3, 1);
+    run<2>("magic round (DADD,DADD,DADD,DADD)", d_out, d_cyc, 0.37, 4);
+    run<3>("rint + DADD + DADD", d_out, d_cyc, 0.37, 3);
+    run<4>("DMUL,F2I.S64,LOP,I2F.F64,DFMA", d_out, d_cyc, 0.37, 5);
+    run<5>("DADD,IADD,LOP,LDS.64,DADD", d_out, d_cyc, 0.37, 5);
+    run<6>("IMAD,LOP,LDS,F2I-lo,IADD", d_out, d_cyc, 0.37, 5);
+    run<7>("DFMA,DFMA (Horner)", d_out, d_cyc, 0.999, 2);
+    double *d_big;
+    cudaMalloc(&d_big, 1024 * sizeof(double));
+    for (int w : {4, 8, 16, 32}) {
+        run_tp<4, 1>("LDS.32 dense", d_big, d_cyc, w);
+        run_tp<8, 1>("LDS.64 dense", d_big, d_cyc, w);
+        run_tp<8, 3>("LDS.64 stride 3 doubles", d_big, d_cyc, w);
+        run_tp<16, 2>("LDS.128 dense", d_big, d_cyc, w);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    printf("status: %s\n", cudaGetErrorString(e));
+    return 0;
+}
