@@ -383,6 +383,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 // named barrier over the consumer warps only (the producer warp never joins)
 __device__ __forceinline__ void consumer_sync(unsigned threads) { asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); }
 
+// peer-memory primitives: system-scope release / acquire on the exchange flags
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 constexpr int kMaxStages = 8;
 constexpr unsigned kBarBytes = 2 * kMaxStages * 8; // full[8], empty[8]
 constexpr unsigned kRedBytes = 32 * 32 * 8;        // consumer-warp reduction scratch [32 warps][32 lanes]
@@ -403,8 +409,10 @@ template <int DIM, int ILP, bool XPP> struct Tune
 
 // ---------------------------------------------------------------- the kernel
 template <int DIM, int ILP, bool STAGED, bool POW2, bool XPP>
-__global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1) backtrace_kernel(const __grid_constant__ BtParams P)
+__global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1)
+    backtrace_kernel(const __grid_constant__ BtParams P, const __grid_constant__ EpilogueParams E)
 {
+    __shared__ unsigned int s_ticket;
     pdl_trigger(); // the slot reduction / field tail behind this launch may be scheduled as soon as an SM has room
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);
@@ -634,6 +642,44 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1) backtrace
 
     if (!P.metrics) {
         flush_tile(cur_tile);
+        if (E.mode) { // ---- epilogue: the last CTA to arrive reduces the slots of all tiles (and pushes them to the peers)
+            __threadfence(); // this CTA's slots are visible device-wide before its ticket
+            consumer_sync(W * 32);
+            if (threadIdx.x == 0) s_ticket = atomicAdd(E.done, 1u);
+            consumer_sync(W * 32);
+            if (s_ticket == E.n_active - 1) {
+                __threadfence();
+                const FinishParams &F = E.F;
+                for (unsigned tile = warp; tile < F.n_tiles; tile += W) { // one warp per tile, lane = node
+                    const unsigned b_lo = (tile * F.rpt) / F.rpc;
+                    const unsigned b_hi = ((tile + 1) * F.rpt - 1) / F.rpc;
+                    double tot = 0; // 8 strided partial sums over the CTAs of the tile, added in order (= finish_rho_kernel)
+                    for (unsigned w = 0; w < 8; ++w) {
+                        double sum = 0;
+                        for (unsigned b = b_lo + w; b <= b_hi; b += 8) {
+                            const unsigned t_first = (b * F.rpc) / F.rpt;
+                            sum += __ldcg(F.slots + (static_cast<size_t>(b) * F.Tmax + (tile - t_first)) * 32 + lane);
+                        }
+                        tot += sum;
+                    }
+                    const unsigned long long l = F.l_first + static_cast<unsigned long long>(tile) * 32 + lane;
+                    if (l <= F.l_last) {
+                        const double val = -F.dV * tot;
+                        F.rho_partial[l] = val;
+                        if (F.rho_full) F.rho_full[l] = 1 - F.dV * tot;
+                        if (E.mode == 2)
+                            for (int p = 0; p < E.X.world; ++p) E.X.data[p][l] = val; // NVLink stores into every GPU's buffer
+                    }
+                }
+                if (E.mode == 2) {
+                    __threadfence_system();
+                    consumer_sync(W * 32);
+                    if (threadIdx.x == 0)
+                        for (int p = 0; p < E.X.world; ++p) st_release_sys(E.X.flag[p], E.X.epoch);
+                }
+                if (threadIdx.x == 0) *E.done = 0; // every participant has arrived: ready for the next launch
+            }
+        }
     } else { // deterministic block reduction of the four metric sums
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -680,12 +726,6 @@ __global__ void __launch_bounds__(256) finish_rho_kernel(const __grid_constant__
             if (F.rho_full) F.rho_full[l] = 1 - F.dV * tot;
         }
     }
-}
-
-// peer-memory primitives: system-scope release / acquire on the exchange flags
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // finish_rho_kernel fused with the peer exchange (multi-GPU step): the tile's rho values are stored straight into the
@@ -831,43 +871,43 @@ __global__ void sample_field_kernel(const __grid_constant__ FieldSampleParams S)
 }
 
 template <int DIM, int ILP, bool STAGED, bool POW2, bool XPP>
-cudaError_t launch_variant(const BtParams &P, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
+cudaError_t launch_variant(const BtParams &P, const EpilogueParams &E, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
 {
     auto kern = backtrace_kernel<DIM, ILP, STAGED, POW2, XPP>;
     if (smem_bytes > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
         if (e != cudaSuccess) return e;
     }
-    kern<<<grid, threads, smem_bytes, st>>>(P);
+    kern<<<grid, threads, smem_bytes, st>>>(P, E);
     return cudaGetLastError();
 }
 
 template <int DIM, int ILP, bool XPP>
-cudaError_t launch_fmt(const BtParams &P, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
+cudaError_t launch_fmt(const BtParams &P, const EpilogueParams &E, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
 {
     if (staged) {
-        return pow2 ? launch_variant<DIM, ILP, true, true, XPP>(P, grid, threads, smem_bytes, st)
-                    : launch_variant<DIM, ILP, true, false, XPP>(P, grid, threads, smem_bytes, st);
+        return pow2 ? launch_variant<DIM, ILP, true, true, XPP>(P, E, grid, threads, smem_bytes, st)
+                    : launch_variant<DIM, ILP, true, false, XPP>(P, E, grid, threads, smem_bytes, st);
     }
-    return pow2 ? launch_variant<DIM, ILP, false, true, XPP>(P, grid, threads, smem_bytes, st)
-                : launch_variant<DIM, ILP, false, false, XPP>(P, grid, threads, smem_bytes, st);
+    return pow2 ? launch_variant<DIM, ILP, false, true, XPP>(P, E, grid, threads, smem_bytes, st)
+                : launch_variant<DIM, ILP, false, false, XPP>(P, E, grid, threads, smem_bytes, st);
 }
 
 template <int DIM, int ILP>
-cudaError_t launch_ilp(const BtParams &P, bool xpp, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
+cudaError_t launch_ilp(const BtParams &P, const EpilogueParams &E, bool xpp, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
 {
     if constexpr (DIM >= 2) {
-        if (xpp) return launch_fmt<DIM, ILP, true>(P, staged, pow2, grid, threads, smem_bytes, st);
+        if (xpp) return launch_fmt<DIM, ILP, true>(P, E, staged, pow2, grid, threads, smem_bytes, st);
     }
-    return launch_fmt<DIM, ILP, false>(P, staged, pow2, grid, threads, smem_bytes, st);
+    return launch_fmt<DIM, ILP, false>(P, E, staged, pow2, grid, threads, smem_bytes, st);
 }
 
 template <int DIM>
-cudaError_t launch_dim(const BtParams &P, int ilp, bool xpp, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes,
+cudaError_t launch_dim(const BtParams &P, const EpilogueParams &E, int ilp, bool xpp, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes,
                        cudaStream_t st)
 {
-    return ilp == 2 ? launch_ilp<DIM, 2>(P, xpp, staged, pow2, grid, threads, smem_bytes, st)
-                    : launch_ilp<DIM, 1>(P, xpp, staged, pow2, grid, threads, smem_bytes, st);
+    return ilp == 2 ? launch_ilp<DIM, 2>(P, E, xpp, staged, pow2, grid, threads, smem_bytes, st)
+                    : launch_ilp<DIM, 1>(P, E, xpp, staged, pow2, grid, threads, smem_bytes, st);
 }
 
 int max_threads_for(int dim, int ilp, bool xpp)
@@ -1024,27 +1064,9 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
         NUFI_CUDA_CHECK(h, cudaMemsetAsync(h->d_mpartials, 0, sizeof(double) * 4 * grid, h->stream));
     }
 
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
-    if (h->kernel_timing) { // off by default: an event between two kernels keeps the second from launching programmatically
-        int rc = ev_acquire(h, &ev_start, &ev_stop);
-        if (rc) return rc;
-        NUFI_CUDA_CHECK(h, cudaEventRecord(ev_start, h->stream));
-    }
-    cudaError_t e;
-    if (h->dim == 1) e = launch_dim<1>(P, ilp, false, staged, pow2, grid, threads, smem_bytes, h->stream);
-    else if (h->dim == 2) e = launch_dim<2>(P, ilp, h->xpp, staged, pow2, grid, threads, smem_bytes, h->stream);
-    else e = launch_dim<3>(P, ilp, h->xpp, staged, pow2, grid, threads, smem_bytes, h->stream);
-    NUFI_CUDA_CHECK(h, e);
-    if (h->kernel_timing) {
-        NUFI_CUDA_CHECK(h, cudaEventRecord(ev_stop, h->stream));
-        h->ev_pending += 1;
-    }
-    h->launches += 1;
-    const char *fmt = h->xpp ? "/xpp" : "";
-    if (staged) std::snprintf(h->variant_buf, sizeof(h->variant_buf), "smem-tma%s/ilp%d/W%u/Lc%dx%d", fmt, ilp, P.W, P.Lc, P.stages);
-    else std::snprintf(h->variant_buf, sizeof(h->variant_buf), "global%s/ilp%d/W%u", fmt, ilp, P.W);
-    h->last_variant = h->variant_buf;
-
+    // ---- slot reduction: by the fused tail (defer), else by the kernel's own last-CTA epilogue (optionally pushing to the peers)
+    EpilogueParams E{};
+    bool tail_reduces = false;
     if (!metrics) {
         FinishParams F{};
         F.slots = h->d_partials;
@@ -1058,9 +1080,41 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
         F.n_tiles = P.n_tiles;
         if (!all_nodes) NUFI_CUDA_CHECK(h, cudaMemsetAsync(h->d_rho_partial, 0, sizeof(double) * h->n_nodes, h->stream));
         h->fin = F;
-        h->fin_pending = true;
-        if (!(defer_finish && whole)) return launch_finish(h);
-        return NUFI_B200_OK;
+        tail_reduces = defer_finish && whole && !h->fin_push;
+        h->fin_pending = tail_reduces;
+        if (!tail_reduces) {
+            E.mode = h->fin_push ? 2 : 1;
+            E.n_active = (P.R + P.rpc - 1) / P.rpc;
+            E.done = h->d_done;
+            E.F = F;
+            if (h->fin_push) E.X = h->px.push;
+        }
+        h->fin_push = false;
+    }
+
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    if (h->kernel_timing) { // off by default: an event between two kernels keeps the second from launching programmatically
+        int rc = ev_acquire(h, &ev_start, &ev_stop);
+        if (rc) return rc;
+        NUFI_CUDA_CHECK(h, cudaEventRecord(ev_start, h->stream));
+    }
+    cudaError_t e;
+    if (h->dim == 1) e = launch_dim<1>(P, E, ilp, false, staged, pow2, grid, threads, smem_bytes, h->stream);
+    else if (h->dim == 2) e = launch_dim<2>(P, E, ilp, h->xpp, staged, pow2, grid, threads, smem_bytes, h->stream);
+    else e = launch_dim<3>(P, E, ilp, h->xpp, staged, pow2, grid, threads, smem_bytes, h->stream);
+    NUFI_CUDA_CHECK(h, e);
+    if (h->kernel_timing) {
+        NUFI_CUDA_CHECK(h, cudaEventRecord(ev_stop, h->stream));
+        h->ev_pending += 1;
+    }
+    h->launches += 1;
+    const char *fmt = h->xpp ? "/xpp" : "";
+    if (staged) std::snprintf(h->variant_buf, sizeof(h->variant_buf), "smem-tma%s/ilp%d/W%u/Lc%dx%d", fmt, ilp, P.W, P.Lc, P.stages);
+    else std::snprintf(h->variant_buf, sizeof(h->variant_buf), "global%s/ilp%d/W%u", fmt, ilp, P.W);
+    h->last_variant = h->variant_buf;
+
+    if (!metrics) {
+        return NUFI_B200_OK; // rho_partial (and rho_full) are complete when the kernel ends, or the tail reduces the slots
     } else {
         finish_metrics_kernel<<<1, 32, 0, h->stream>>>(h->d_mpartials, grid, h->d_metrics);
         NUFI_CUDA_CHECK(h, cudaGetLastError());

@@ -145,6 +145,18 @@ struct PeerState
     PeerRecv recv{};
 };
 
+// In-kernel epilogue of the backtrace kernel (rho mode): the last CTA to finish adds the slots of every tile in a fixed order
+// (what finish_rho_kernel does as a separate launch) and, in a multi-GPU step, stores the result into every GPU's exchange
+// buffer and releases this rank's flags there (finish_push_kernel).  mode 0: none -- the fused tail reduces the slots itself.
+struct EpilogueParams
+{
+    int mode;                 // 0 none, 1 finish, 2 finish + push to the peers
+    unsigned int n_active;    // CTAs that take part (blockIdx.x < n_active)
+    unsigned int *done;       // device counter, zero between launches
+    FinishParams F;
+    PeerPush X;
+};
+
 struct Handle
 {
     int dim = 0, order = 4, device = 0;
@@ -194,6 +206,7 @@ struct Handle
     bool pdl = true;             // programmatic dependent launch of finish / tail behind the backtrace kernel (NUFI_B200_PDL=0: off)
     int sm_count = 148;
     size_t smem_optin = 0;
+    unsigned int *d_done = nullptr; // arrival counter of the backtrace kernel's last-CTA epilogue
     unsigned long long vstride = 1, voff = 0; // velocity share of the next backtrace launch (multi-GPU step), else 1, 0
     PeerState px;
     bool fin_push = false;       // the pending slot reduction also pushes to the peers (finish_push_kernel)

@@ -6,8 +6,11 @@ tests/golden/fullsize_<case>.npz and checked against the GPU's free run by tests
 
     python tests/golden/make_fullsize_traces.py [C1 C2 C3 C4]
 
-The `_fast` build (-O3 -march=x86-64-v3) is used: same source, FMA contraction allowed -- its rounding differs from the
-canonical -O2 build at the 1e-16 level per operation, far below the 1e-8 gate; the script records which build made the trace.
+The `_fast` build (-O3 -march=x86-64-v3) makes the main traces: same source, FMA contraction allowed -- its rounding differs
+from the canonical -O2 -ffp-contract=off build at the 1e-16 level per operation.  `--canonical` writes a second trace
+(fullsize_<case>_canonical.npz) with that build: the spread between the two is the reference's OWN sensitivity to rounding
+over the run (chaotic two-stream: it grows to O(1e-2); weak Landau: the signal decays 13 orders of magnitude into the rounding
+floor), which bounds how tightly any other implementation can be compared at each step.
 """
 import os
 import sys
@@ -27,8 +30,11 @@ STEPS = {"C1": 1600, "C2": 1600, "C3": 40, "C4": 50}
 
 
 def main():
-    names = sys.argv[1:] or ["C4", "C3", "C1", "C2"]
-    variant = "_fast" if Reference.available("_fast") else ""
+    args = sys.argv[1:]
+    canonical = "--canonical" in args  # the reference-like -O2 -ffp-contract=off build: a second, independently rounded trace
+    names = [a for a in args if not a.startswith("--")] or ["C4", "C3", "C1", "C2"]
+    variant = "" if canonical else ("_fast" if Reference.available("_fast") else "")
+    suffix = "_canonical" if canonical else ""
     ref = Reference(variant)
     for name in names:
         conf, f0, _, desc = make_workload(name, 1)
@@ -37,7 +43,7 @@ def main():
         coeffs, energy, rho = ref.run(conf, f0, nt)
         dt = time.time() - t0
         st = coeffs.size // nt
-        np.savez_compressed(os.path.join(HERE, f"fullsize_{name}.npz"), energy=energy, steps=np.int64(nt), rho_last=rho,
+        np.savez_compressed(os.path.join(HERE, f"fullsize_{name}{suffix}.npz"), energy=energy, steps=np.int64(nt), rho_last=rho,
                             level_last=coeffs[(nt - 1) * st: nt * st], workload=np.array(desc), f0_kind=np.int64(f0.kind),
                             f0_p=np.array(list(f0.p)), build=np.array(os.path.basename(ref.path)), threads=np.int64(ref.threads()),
                             seconds=np.float64(dt))
