@@ -650,26 +650,46 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1)
             if (s_ticket == E.n_active - 1) {
                 __threadfence();
                 const FinishParams &F = E.F;
-                for (unsigned tile = warp; tile < F.n_tiles; tile += W) { // one warp per tile, lane = node
-                    const unsigned b_lo = (tile * F.rpt) / F.rpc;
-                    const unsigned b_hi = ((tile + 1) * F.rpt - 1) / F.rpc;
-                    double tot = 0; // 8 strided partial sums over the CTAs of the tile, added in order (= finish_rho_kernel)
-                    for (unsigned w = 0; w < 8; ++w) {
+                // Batches of 4 tiles = 32 (tile, w) tasks spread over the consumer warps: task (tile, w) adds the slots of CTAs
+                // b_lo+w, b_lo+w+8, ... (loads issued four at a time, so a task costs about one L2 round trip); then one warp per
+                // tile adds the 8 partial sums in order -- the association of finish_rho_kernel.
+                for (unsigned t0 = 0; t0 < F.n_tiles; t0 += 4) {
+                    for (unsigned task = warp; task < 32; task += W) {
+                        const unsigned tile = t0 + (task >> 3), w = task & 7;
                         double sum = 0;
-                        for (unsigned b = b_lo + w; b <= b_hi; b += 8) {
-                            const unsigned t_first = (b * F.rpc) / F.rpt;
-                            sum += __ldcg(F.slots + (static_cast<size_t>(b) * F.Tmax + (tile - t_first)) * 32 + lane);
+                        if (tile < F.n_tiles) {
+                            const unsigned b_lo = (tile * F.rpt) / F.rpc;
+                            const unsigned b_hi = ((tile + 1) * F.rpt - 1) / F.rpc;
+                            for (unsigned b = b_lo + w; b <= b_hi; b += 32) {
+                                double v[4];
+#pragma unroll
+                                for (unsigned u = 0; u < 4; ++u) {
+                                    const unsigned bb = b + 8 * u;
+                                    const unsigned t_first = (bb * F.rpc) / F.rpt;
+                                    v[u] = bb <= b_hi ? __ldcg(F.slots + (static_cast<size_t>(bb) * F.Tmax + (tile - t_first)) * 32 + lane) : 0.0;
+                                }
+                                sum = (((sum + v[0]) + v[1]) + v[2]) + v[3]; // + 0.0 is exact: same order as one-by-one
+                            }
                         }
-                        tot += sum;
+                        sred[task][lane] = sum;
                     }
-                    const unsigned long long l = F.l_first + static_cast<unsigned long long>(tile) * 32 + lane;
-                    if (l <= F.l_last) {
-                        const double val = -F.dV * tot;
-                        F.rho_partial[l] = val;
-                        if (F.rho_full) F.rho_full[l] = 1 - F.dV * tot;
-                        if (E.mode == 2)
-                            for (int p = 0; p < E.X.world; ++p) E.X.data[p][l] = val; // NVLink stores into every GPU's buffer
+                    consumer_sync(W * 32);
+                    for (unsigned k = warp; k < 4; k += W) {
+                        const unsigned tile = t0 + k;
+                        if (tile >= F.n_tiles) continue;
+                        double tot = 0;
+#pragma unroll
+                        for (int w = 0; w < 8; ++w) tot += sred[8 * k + w][lane];
+                        const unsigned long long l = F.l_first + static_cast<unsigned long long>(tile) * 32 + lane;
+                        if (l <= F.l_last) {
+                            const double val = -F.dV * tot;
+                            F.rho_partial[l] = val;
+                            if (F.rho_full) F.rho_full[l] = 1 - F.dV * tot;
+                            if (E.mode == 2)
+                                for (int p = 0; p < E.X.world; ++p) E.X.data[p][l] = val; // NVLink stores into every GPU's buffer
+                        }
                     }
+                    consumer_sync(W * 32);
                 }
                 if (E.mode == 2) {
                     __threadfence_system();

@@ -429,9 +429,15 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
         const FinishParams &F = S.F;
         auto slot_sum = [&](unsigned tile, unsigned lane, unsigned b_lo, unsigned b_hi, int w) {
             double sum = 0;
-            for (unsigned b = b_lo + w; b <= b_hi; b += 8) {
-                const unsigned t_first = (b * F.rpc) / F.rpt;
-                sum += F.slots[(static_cast<size_t>(b) * F.Tmax + (tile - t_first)) * 32 + lane];
+            for (unsigned b = b_lo + w; b <= b_hi; b += 32) { // four loads in flight per trip; + 0.0 is exact, the order is kept
+                double v[4];
+#pragma unroll
+                for (unsigned u = 0; u < 4; ++u) {
+                    const unsigned bb = b + 8 * u;
+                    const unsigned t_first = (bb * F.rpc) / F.rpt;
+                    v[u] = bb <= b_hi ? F.slots[(static_cast<size_t>(bb) * F.Tmax + (tile - t_first)) * 32 + lane] : 0.0;
+                }
+                sum = (((sum + v[0]) + v[1]) + v[2]) + v[3];
             }
             return sum;
         };
