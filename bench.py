@@ -147,6 +147,32 @@ def reference_sweep_timer(conf, f0, n, coeffs, budget_s: float):
     return run, float(l_n) * nv * max(n, 1), desc, impl.kind, threads, l_n, out
 
 
+def reference_cuda_leg(conf, f0, n, coeffs_host, sched, device, reps=3):
+    """Informational (north star: 'the reference's existing CUDA path'): the reference's own nufi/cuda_kernel.cu, compiled
+    unmodified for sm_100a (oracle/_ref/libnufi_refcuda.so), timed with CUDA events on the same GPU, same history, same step.
+    Its f0 is the one committed in the reference's config.hpp; where that is this workload's f0 (C2) rho is compared too."""
+    try:
+        from oracle.oracle_py import ReferenceCuda
+        from numericalflowiteration_b200 import n_quad
+
+        if not ReferenceCuda.available():
+            return {"unavailable": "oracle/_ref/libnufi_refcuda.so not built"}
+        rc = ReferenceCuda(conf, device)
+        rc.upload(coeffs_host, n)
+        rho, ms = rc.rho(n, reps)
+        rc.close()
+        out = {"value": float(n_quad(conf)) * n / (ms * 1e-3), "unit": "point-steps/s", "kernel_ms": ms, "reps": reps,
+               "what": "reference nufi/cuda_kernel.cu (cuda_kernel<double,4>::compute_rho: memset + cuda_eval_rho, 64-thread blocks, "
+                       "atomicAdd), compiled unmodified for sm_100a, CUDA-event timed on this GPU at the same depth"}
+        same_f0 = conf.dim == 1 and f0.kind == 1 and list(f0.p)[:2] == [0.01, 0.5]
+        if same_f0:
+            ours = sched.eval_rho(n)
+            out["rho_rel_linf_ours_vs_reference_cuda"] = float(np.max(np.abs(ours - rho)) / np.max(np.abs(rho)))
+        return out
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -427,6 +453,9 @@ def run_gpu_arm(args):
             want = out["rho"][:l_n]
             parity = {"rho_rel_linf_vs_cpu_reference": float(np.max(np.abs(got[:l_n] - want)) / np.max(np.abs(want))),
                       "nodes_checked": int(l_n), "tolerance": 1e-10}
+        ref_cuda = None
+        if world == 1 and not args.no_cpu:
+            ref_cuda = reference_cuda_leg(conf, f0, n, coeffs_host, s, local, reps=3)
         line = {
             "metric": "backtrace point-steps/sec", "value": value, "unit": "point-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["t_ms"] / args.steps, "higher_is_better": True,
@@ -438,7 +467,7 @@ def run_gpu_arm(args):
                                        ("stores into NVLink peer memory fused into the slot-reduction and tail kernels (no collective call)"
                                         if runner.exchange == "peer-memory" else "NCCL all-reduce")) if world > 1 else "1 GPU",
                        "exchange": runner.exchange, "exchange_note": runner.exchange_note},
-            "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "reference_cuda": ref_cuda,
             "e2e": {"value": e2e_value, "unit": "point-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps,
                     "path": "upload_phi(n-1) -> compute_rho -> download_rho -> solve_interpolate_host, host buffers, wall clock"},
@@ -458,9 +487,18 @@ def run_gpu_arm(args):
                 m2 = measure_gpu(r2, d2, k, 3, flush, torch, dist)
                 ps = float(n_quad(c2)) * d2
                 tf = ps * FLOP_PER_POINT_STEP[c2.dim] / (m2["bt_ms"] * 1e-3) / 1e12
-                extras.append({"workload": desc2, "depth_n": d2, "point_steps_per_s": ps * k / (m2["t_ms"] * 1e-3),
-                               "ms_per_step": m2["t_ms"] / k, "kernel_ms": m2["bt_ms"], "variant": r2.s.last_variant,
-                               "fp64_tflops": tf, "fp64_frac": tf / line["roofline"]["peak"]})
+                ex = {"workload": desc2, "depth_n": d2, "point_steps_per_s": ps * k / (m2["t_ms"] * 1e-3),
+                      "ms_per_step": m2["t_ms"] / k, "kernel_ms": m2["bt_ms"], "variant": r2.s.last_variant,
+                      "fp64_tflops": tf, "fp64_frac": tf / line["roofline"]["peak"]}
+                if not args.no_cpu and not (c2.dim == 3 and c2.Nx >= 32):  # the reference kernel needs ~10 s per call on C5-32
+                    st2 = stride_t(c2)
+                    hist2 = np.zeros((d2 + 1) * st2)
+                    for lvl in range(d2):
+                        hist2[lvl * st2:(lvl + 1) * st2] = r2.s.download_phi(lvl)
+                    rc2 = reference_cuda_leg(c2, f2, d2, hist2, r2.s, local, reps=2)
+                    ex["reference_cuda_point_steps_per_s"] = rc2.get("value")
+                    ex["reference_cuda_kernel_ms"] = rc2.get("kernel_ms")
+                extras.append(ex)
                 r2.s.close()
             except Exception as e:  # noqa: BLE001
                 extras.append({"workload": name, "error": repr(e)})

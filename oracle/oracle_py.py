@@ -257,6 +257,47 @@ class Reference:
         return coeffs, energy, rho
 
 
+class ReferenceCuda:
+    """The reference's own CUDA path (nufi/cuda_kernel.cu compiled unmodified for sm_100a, oracle/_ref/libnufi_refcuda.so):
+    the informational GPU baseline of bench.py.  f0 is the one committed in the reference's config.hpp."""
+
+    kind = "reference-cuda"
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(os.path.join(HERE, "_ref", "libnufi_refcuda.so"))
+
+    def __init__(self, conf, device: int = 0):
+        self.lib = L = C.CDLL(os.path.join(HERE, "_ref", "libnufi_refcuda.so"))
+        self.conf, self.d = conf, conf.dim
+        for nm, args, res in (("create", [_p, _i], _p), ("destroy", [_p], None), ("upload", [_p, _sz, _dp], _i),
+                              ("rho", [_p, _sz, _sz, _sz, _dp, _i, C.POINTER(C.c_float)], _i)):
+            f = getattr(L, f"refcuda_{nm}_{self.d}d")
+            f.argtypes, f.restype = args, res
+        self.h = getattr(L, f"refcuda_create_{self.d}d")(C.addressof(conf), device)
+        if not self.h:
+            raise RuntimeError("reference cuda_kernel could not be created")
+
+    def upload(self, coeffs, n_levels: int):
+        if getattr(self.lib, f"refcuda_upload_{self.d}d")(self.h, n_levels, np.ascontiguousarray(coeffs)) != 0:
+            raise RuntimeError("reference upload_phi failed")
+
+    def rho(self, n: int, reps: int = 3):
+        """(rho in the CPU convention 1 + partial, ms per compute_rho call) over the whole quadrature range."""
+        N = _nodes(self.conf)
+        nq = N * int(np.prod([getattr(self.conf, k) for k in ("Nu", "Nv", "Nw")[: self.d]]))
+        out = np.zeros(N)
+        ms = C.c_float(0)
+        if getattr(self.lib, f"refcuda_rho_{self.d}d")(self.h, n, 0, nq, out, reps, C.byref(ms)) != 0:
+            raise RuntimeError("reference compute_rho failed")
+        return 1.0 + out, float(ms.value)
+
+    def close(self):
+        if self.h:
+            getattr(self.lib, f"refcuda_destroy_{self.d}d")(self.h)
+            self.h = None
+
+
 def synthetic_history(conf, n_levels: int, seed: int = 1234, amp: float = 1e-2, order: int = 4) -> np.ndarray:
     """Smooth random-amplitude sine potentials interpolated to spline levels, in the spirit of the reference's
     isolated-step harness (bin/test_nufi_cpu_3d_isolated.cpp:76-105): level m holds the interpolant of

@@ -44,7 +44,9 @@ template <int WIDTH, int STRIDE> __global__ void lds_tp(double *out, long long *
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int idx = ((base + u * 40) & 2047) + lane * STRIDE;
+            // STRIDE > 0: lane i at i*STRIDE doubles; 0: all lanes one address; < 0: groups of -STRIDE lanes share an address,
+            // consecutive groups one cell (2 doubles for the 128-bit case) apart
+            const int idx = ((base + u * 40) & 2047) + (STRIDE >= 0 ? lane * STRIDE : (lane / (STRIDE < 0 ? -STRIDE : 1)) * (WIDTH == 16 ? 2 : 1));
             if (WIDTH == 4) {
                 acc0 += reinterpret_cast<const float *>(smd)[idx];
             } else if (WIDTH == 8) {
@@ -105,6 +107,14 @@ int main()
         run_tp<8, 1>("LDS.64 dense", d_big, d_cyc, w);
         run_tp<8, 3>("LDS.64 stride 3 doubles", d_big, d_cyc, w);
         run_tp<16, 2>("LDS.128 dense", d_big, d_cyc, w);
+        if (w == 16) { // lanes of a warp (nearly) co-located: what a velocity-fastest lane layout reads at shallow history depth
+            run_tp<8, 0>("LDS.64 all lanes same address", d_big, d_cyc, w);
+            run_tp<16, 0>("LDS.128 all lanes same address", d_big, d_cyc, w);
+            run_tp<8, -4>("LDS.64 lanes in groups of 4", d_big, d_cyc, w);
+            run_tp<16, -4>("LDS.128 lanes in groups of 4", d_big, d_cyc, w);
+            run_tp<8, -2>("LDS.64 lanes in groups of 2", d_big, d_cyc, w);
+            run_tp<16, -2>("LDS.128 lanes in groups of 2", d_big, d_cyc, w);
+        }
     }
     cudaError_t e = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(e));
