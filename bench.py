@@ -29,6 +29,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FLOP_PER_POINT_STEP = {1: 30.0, 2: 138.0, 3: 431.0}  # SURVEY.md section 8d / App. A.4 (algorithmic, FMA = 2)
+SMEM_BYTES_PER_POINT_STEP = {1: 24.0, 2: 128.0, 3: 512.0}  # coefficients a point gathers per level
+SMEM_BYTES_PER_CLK_SM = 128.0  # shared-memory data pipe; tools/microbench.cu measures 125-127 on this GPU
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -427,6 +429,9 @@ def run_gpu_arm(args):
         except Exception:  # noqa: BLE001
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        props = torch.cuda.get_device_properties(local)
+        s_sm_count = props.multi_processor_count
+        sm_mhz_peak = float(peaks.get("sm_max_mhz", 1965.0))
         roofline = {
             "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
             "traffic": None,
@@ -436,6 +441,11 @@ def run_gpu_arm(args):
             "how": "second timed region of the same K steps with a CUDA event pair around every backtrace launch (library stream)",
             "flop_per_point_step": FLOP_PER_POINT_STEP[dim],
             "peak_source": "measured live: register-only DFMA loop (nufi_b200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+            "smem": {"achieved": my_psteps * SMEM_BYTES_PER_POINT_STEP[dim] / (m["bt_ms"] * 1e-3) / 1e9,
+                     "peak": SMEM_BYTES_PER_CLK_SM * s_sm_count * sm_mhz_peak * 1e6 / 1e9, "unit": "GB/s",
+                     "frac": my_psteps * SMEM_BYTES_PER_POINT_STEP[dim] / (m["bt_ms"] * 1e-3) / (SMEM_BYTES_PER_CLK_SM * s_sm_count * sm_mhz_peak * 1e6),
+                     "note": "the co-limiting unit (DESIGN.md 3.1): algorithmic shared-memory bytes gathered per point-step x point-steps/s "
+                             "against 128 B/clk/SM x SMs x max SM clock; bank-conflict replays (C2) are not counted as achieved"},
             "hbm": {"achieved": hist_bytes / (m["bt_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": hist_bytes / (m["bt_ms"] * 1e-3) / 1e9 / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",

@@ -33,7 +33,12 @@ def main():
     w = csv.writer(sys.stdout)
     w.writerow(["report", "kernel", "metric", "unit", "value"])
     for rep in sys.argv[1:]:
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+        if rep.endswith(".csv.gz"):  # a raw page exported on the GPU box (tools/gpu_round.sh)
+            import gzip
+
+            raw = gzip.open(rep, "rt").read()
+        else:
+            raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         hdr, units = rows[0], rows[1]
         for vals in rows[2:]:
