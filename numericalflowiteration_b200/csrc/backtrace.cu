@@ -383,10 +383,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 // named barrier over the consumer warps only (the producer warp never joins)
 __device__ __forceinline__ void consumer_sync(unsigned threads) { asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); }
 
-// peer-memory primitives: system-scope release / acquire on the exchange flags
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+// peer-memory primitive: the exchange flags are raised with fence.sys + relaxed system-scope store, read with ld.acquire.sys;
+// after a fence.sys by the same thread a relaxed system-scope store completes the release pattern (PTX memory model)
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v)
 {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 constexpr int kMaxStages = 8;
@@ -643,12 +644,16 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1)
     if (!P.metrics) {
         flush_tile(cur_tile);
         if (E.mode) { // ---- epilogue: the last CTA to arrive reduces the slots of all tiles (and pushes them to the peers)
-            __threadfence(); // this CTA's slots are visible device-wide before its ticket
-            consumer_sync(W * 32);
-            if (threadIdx.x == 0) s_ticket = atomicAdd(E.done, 1u);
+            // (flush_tile ended with a barrier over the consumer warps: thread 0 has observed every slot store of this CTA, so its
+            //  one cumulative fence orders them all before the ticket -- the pattern of cooperative-groups grid sync.  A fence in
+            //  every thread costs microseconds here, and tens of them at system scope below.)
+            if (threadIdx.x == 0) {
+                __threadfence();
+                s_ticket = atomicAdd(E.done, 1u);
+                __threadfence();
+            }
             consumer_sync(W * 32);
             if (s_ticket == E.n_active - 1) {
-                __threadfence();
                 const FinishParams &F = E.F;
                 // Batches of 4 tiles = 32 (tile, w) tasks spread over the consumer warps: task (tile, w) adds the slots of CTAs
                 // b_lo+w, b_lo+w+8, ... (loads issued four at a time, so a task costs about one L2 round trip); then one warp per
@@ -691,11 +696,11 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1)
                     }
                     consumer_sync(W * 32);
                 }
-                if (E.mode == 2) {
-                    __threadfence_system();
-                    consumer_sync(W * 32);
-                    if (threadIdx.x == 0)
-                        for (int p = 0; p < E.X.world; ++p) st_release_sys(E.X.flag[p], E.X.epoch);
+                if (E.mode == 2) { // the batch loop ended with a barrier: lanes 0..world-1 of warp 0 have observed all remote stores
+                    if (warp == 0) {
+                        __threadfence_system(); // ONE system-scope fence (warp 0), then the flags go out to all peers in parallel
+                        if (lane < E.X.world) st_relaxed_sys(E.X.flag[lane], E.X.epoch);
+                    }
                 }
                 if (threadIdx.x == 0) *E.done = 0; // every participant has arrived: ready for the next launch
             }
@@ -782,14 +787,14 @@ __global__ void __launch_bounds__(256) finish_push_kernel(const __grid_constant_
             }
         }
     }
-    __threadfence_system(); // this block's remote stores are visible system-wide before its ticket
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system(); // cumulative: this block's remote stores (observed through the barrier) before its ticket
         const unsigned t = atomicAdd(X.ticket, 1u);
         if (t == gridDim.x - 1) { // every block has stored and fenced
             *X.ticket = 0;
             __threadfence_system();
-            for (int p = 0; p < X.world; ++p) st_release_sys(X.flag[p], X.epoch);
+            for (int p = 0; p < X.world; ++p) st_relaxed_sys(X.flag[p], X.epoch);
         }
     }
 }
