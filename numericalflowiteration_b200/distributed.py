@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["partition", "DistributedStepper", "attach_peers"]
+__all__ = ["partition", "velocity_share", "DistributedStepper", "attach_peers"]
 
 
 def partition(n_total: int, n_parts: int, part: int, begin: int = 0) -> tuple[int, int]:
@@ -19,6 +19,13 @@ def partition(n_total: int, n_parts: int, part: int, begin: int = 0) -> tuple[in
     lo = begin + part * chunk + min(part, rem)
     hi = lo + chunk + (1 if part < rem else 0)
     return lo, hi
+
+
+def velocity_share(n_vel: int, n_parts: int, part: int) -> range:
+    """Velocity nodes rank ``part`` traces in the fused multi-GPU step (``peer_step`` / ``group_step``): every
+    ``n_parts``-th node starting at ``part``, for EVERY spatial node -- all GPUs integrate statistically identical samples of
+    phase space (csrc/peer.cu).  Flat quadrature indices of the share: ``q = l * n_vel + j`` for ``j`` in the range."""
+    return range(part, n_vel, n_parts)
 
 
 class DistributedStepper:

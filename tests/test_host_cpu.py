@@ -134,6 +134,22 @@ g = [None] * world
 dist.all_gather_object(g, total.tobytes())
 assert all(x == g[0] for x in g)
 print(f"rank {rank}/{world} q=[{lo},{hi}) err={err:.1e}")
+# the fused multi-GPU step shards by interleaved velocity nodes instead (csrc/peer.cu): rank r takes nodes r, r+world, ...
+from numericalflowiteration_b200 import n_nodes, n_vel
+from numericalflowiteration_b200.distributed import velocity_share
+nv, nn = n_vel(conf), n_nodes(conf)
+mine = velocity_share(nv, world, rank)
+shares = [None] * world
+dist.all_gather_object(shares, list(mine))
+assert sorted(j for sh in shares for j in sh) == list(range(nv))          # disjoint, complete
+part2 = np.zeros(nn)
+for l in range(0, nn, 7):                                                    # a sample of the nodes keeps this quick
+    for j in mine:
+        part2 = orc.rho_partial(conf, f0, 6, coeffs, l * nv + j, l * nv + j + 1, rho=part2)
+total2 = host_allreduce_partials(dist, part2)
+err2 = float(np.max(np.abs(1 + total2[::7] - want[::7])) / np.max(np.abs(want)))
+assert err2 <= 1e-13, err2
+print(f"rank {rank}/{world} velocity share {mine} err={err2:.1e}")
 dist.destroy_process_group()
 '''
 
