@@ -226,6 +226,11 @@ int nufi_b200_backtrace_time(nufi_b200_handle *h, double *total_ms, uint64_t *co
 const char *nufi_b200_last_variant(const nufi_b200_handle *h);
 /* force a variant for A/B tests: 0 auto, 1 global-memory path, 2 shared-memory staged path */
 int nufi_b200_set_variant(nufi_b200_handle *h, int variant);
+/* lane layout of the backtrace kernel: nodes per tile = 32 (every lane of a warp its own spatial node, x-neighbours, one
+ * velocity: rigid drift, conflict-free at any history depth) or 16/8/4/2/1 (32/TN lanes per node with neighbouring velocities:
+ * their loads coincide early in the history and are served as broadcasts -- the lane layout of the reference's kernel,
+ * nufi/cuda_kernel.cu:40-41, is TN = 1).  0 = automatic. */
+int nufi_b200_set_tile_nodes(nufi_b200_handle *h, int nodes_per_tile);
 /* field-tail implementation: 0 auto (fused single-CTA kernel for grids up to 4096 nodes, cuFFT otherwise),
  * 1 cuFFT D2Z + symbol + Z2D + expand, 2 fused single-CTA kernel */
 int nufi_b200_set_tail_variant(nufi_b200_handle *h, int variant);

@@ -604,6 +604,17 @@ int nufi_b200_set_variant(nufi_b200_handle *h, int variant)
     return NUFI_B200_OK;
 }
 
+int nufi_b200_set_tile_nodes(nufi_b200_handle *h, int nodes_per_tile)
+{
+    Handle *hh = H(h);
+    if (!hh) return fail(nullptr, NUFI_B200_ERR_ARG, "handle is NULL");
+    const int t = nodes_per_tile;
+    if (!(t == 0 || t == 1 || t == 2 || t == 4 || t == 8 || t == 16 || t == 32))
+        return fail(hh, NUFI_B200_ERR_ARG, "nodes per tile must be 0 (automatic), 1, 2, 4, 8, 16 or 32");
+    hh->tn_force = t;
+    return NUFI_B200_OK;
+}
+
 int nufi_b200_set_tail_variant(nufi_b200_handle *h, int variant)
 {
     Handle *hh = H(h);

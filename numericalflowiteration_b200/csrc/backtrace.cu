@@ -484,7 +484,9 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1)
         if (warp == 0) {
             double sum = 0;
             for (unsigned w = 0; w < W; ++w) sum += sred[w][lane];
-            P.slots[(static_cast<size_t>(blockIdx.x) * P.Tmax + (tile - t_first)) * 32 + lane] = sum;
+            // TN < 32: the 32/TN lanes that traced the same node (lane % TN) are combined by a fixed shuffle tree
+            for (unsigned off = 16; off >= P.TN; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
+            P.slots[(static_cast<size_t>(blockIdx.x) * P.Tmax + (tile - t_first)) * 32 + lane] = static_cast<unsigned>(lane) < P.TN ? sum : 0.0;
         }
         consumer_sync(W * 32);
         acc = 0;
@@ -512,7 +514,8 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1)
             continue;
         }
 
-        unsigned long long l = P.l_first + static_cast<unsigned long long>(tile) * 32 + lane;
+        unsigned long long l = P.l_first + static_cast<unsigned long long>(tile) * P.TN + (lane & (P.TN - 1));
+        const unsigned vsub = static_cast<unsigned>(lane) >> P.TNlog2, G = 32u >> P.TNlog2; // velocity sub-index within the warp-unit
         const bool node_ok = l <= P.l_last;
         if (!node_ok) l = P.l_first;
         int ix, iy = 0, iz = 0;
@@ -532,6 +535,7 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1)
         for (int i = 0; i < ILP; ++i) {
             unsigned long long j = P.interleave ? static_cast<unsigned long long>(jc) + static_cast<unsigned long long>(i) * P.upt
                                                 : static_cast<unsigned long long>(jc) * ILP + i;
+            j = j * G + vsub; // the 32/TN lanes of a node take neighbouring velocities: early in the history they share cells
             ok[i] = node_ok && j < P.Nvel_loc;
             if (j >= P.Nvel_loc) j = 0;
             j = j * P.vstride + P.voff; // this GPU's share of the velocity nodes (multi-GPU step: every vstride-th one)
@@ -685,8 +689,8 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1)
                         double tot = 0;
 #pragma unroll
                         for (int w = 0; w < 8; ++w) tot += sred[8 * k + w][lane];
-                        const unsigned long long l = F.l_first + static_cast<unsigned long long>(tile) * 32 + lane;
-                        if (l <= F.l_last) {
+                        const unsigned long long l = F.l_first + static_cast<unsigned long long>(tile) * F.TN + lane;
+                        if (static_cast<unsigned>(lane) < F.TN && l <= F.l_last) {
                             const double val = -F.dV * tot;
                             F.rho_partial[l] = val;
                             if (F.rho_full) F.rho_full[l] = 1 - F.dV * tot;
@@ -745,8 +749,8 @@ __global__ void __launch_bounds__(256) finish_rho_kernel(const __grid_constant__
         double tot = 0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) tot += part[w][lane];
-        const unsigned long long l = F.l_first + static_cast<unsigned long long>(tile) * 32 + lane;
-        if (l <= F.l_last) {
+        const unsigned long long l = F.l_first + static_cast<unsigned long long>(tile) * F.TN + lane;
+        if (static_cast<unsigned>(lane) < F.TN && l <= F.l_last) {
             F.rho_partial[l] = -F.dV * tot;
             if (F.rho_full) F.rho_full[l] = 1 - F.dV * tot;
         }
@@ -778,8 +782,8 @@ __global__ void __launch_bounds__(256) finish_push_kernel(const __grid_constant_
             double tot = 0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) tot += part[w][lane];
-            const unsigned long long l = F.l_first + static_cast<unsigned long long>(tile) * 32 + lane;
-            if (l <= F.l_last) {
+            const unsigned long long l = F.l_first + static_cast<unsigned long long>(tile) * F.TN + lane;
+            if (static_cast<unsigned>(lane) < F.TN && l <= F.l_last) {
                 const double val = -F.dV * tot;
                 F.rho_partial[l] = val;
                 if (F.rho_full) F.rho_full[l] = 1 - F.dV * tot;
@@ -1000,7 +1004,21 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     P.l_first = q_begin / P.Nvel;
     P.l_last = (q_end - 1) / P.Nvel;
     const unsigned long long n_nodes_range = P.l_last - P.l_first + 1;
-    P.n_tiles = static_cast<unsigned>((n_nodes_range + 31) / 32);
+    // nodes per tile: 32 = every lane its own node (rigid drift, conflict-free at any depth); fewer = 32/TN lanes per node with
+    // neighbouring velocities, whose window loads coincide early in the history and are served as broadcasts (short 3d histories)
+    unsigned TN = 32;
+    {
+        const int want = env_int("NUFI_B200_TN", 0);
+        if (want == 1 || want == 2 || want == 4 || want == 8 || want == 16 || want == 32) TN = static_cast<unsigned>(want);
+        else if (h->tn_force) TN = static_cast<unsigned>(h->tn_force);
+    }
+    P.TN = TN;
+    P.TNlog2 = 0;
+    while ((1u << P.TNlog2) < TN) ++P.TNlog2;
+    const unsigned G = 32u / TN;
+    const unsigned long long n_tiles64 = (n_nodes_range + TN - 1) / TN;
+    if (n_tiles64 >= (1ull << 31)) return fail(h, NUFI_B200_ERR_RANGE, "too many tiles for one launch");
+    P.n_tiles = static_cast<unsigned>(n_tiles64);
     P.level_bytes = static_cast<unsigned>(h->level_stride * 8);
 
     // ---- variant: stage the history through shared memory when at least two levels fit
@@ -1042,7 +1060,7 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
             // 3d: one point per thread at 128 registers (16 warps) beats two points at 255 (8 warps) -- measured
             if (!force_ilp && h->dim == 3 && ilp == 2) continue;
             const unsigned wmax = max_threads_for(h->dim, ilp, h->xpp) / 32 - (staged ? 1 : 0);
-            const unsigned long long upt = (P.Nvel_loc + ilp - 1) / ilp;
+            const unsigned long long upt = ((P.Nvel_loc + G - 1) / G + ilp - 1) / ilp;
             for (unsigned W = 1; W <= wmax; ++W) {
                 if (force_w && static_cast<int>(W) != force_w) continue;
                 const unsigned long long rpt = (upt + W - 1) / W;
@@ -1061,7 +1079,7 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     }
     const int ilp = best_ilp;
     P.W = best_W;
-    P.upt = static_cast<unsigned>((P.Nvel_loc + ilp - 1) / ilp);
+    P.upt = static_cast<unsigned>(((P.Nvel_loc + G - 1) / G + ilp - 1) / ilp);
     P.rpt = (P.upt + P.W - 1) / P.W;
     const unsigned long long R64 = static_cast<unsigned long long>(P.rpt) * P.n_tiles;
     if (R64 >= (1ull << 31)) return fail(h, NUFI_B200_ERR_RANGE, "quadrature range too large for one launch");
@@ -1103,18 +1121,23 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
         F.l_first = P.l_first; F.l_last = P.l_last;
         F.rpt = P.rpt; F.rpc = P.rpc; F.Tmax = P.Tmax;
         F.n_tiles = P.n_tiles;
+        F.TN = P.TN;
         if (!all_nodes) NUFI_CUDA_CHECK(h, cudaMemsetAsync(h->d_rho_partial, 0, sizeof(double) * h->n_nodes, h->stream));
         h->fin = F;
         tail_reduces = defer_finish && whole && !h->fin_push;
         h->fin_pending = tail_reduces;
-        if (!tail_reduces) {
+        // many tiles (TN < 32 on a large grid): the one-CTA epilogue would serialise them; use the multi-block finish kernels
+        const bool epilogue = P.n_tiles <= 256;
+        if (!tail_reduces && !epilogue) {
+            h->fin_pending = true; // launch_finish() below runs finish_rho_kernel / finish_push_kernel (h->fin_push kept)
+        } else if (!tail_reduces) {
             E.mode = h->fin_push ? 2 : 1;
             E.n_active = (P.R + P.rpc - 1) / P.rpc;
             E.done = h->d_done;
             E.F = F;
             if (h->fin_push) E.X = h->px.push;
         }
-        h->fin_push = false;
+        if (tail_reduces || epilogue) h->fin_push = false;
     }
 
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -1134,11 +1157,14 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     }
     h->launches += 1;
     const char *fmt = h->xpp ? "/xpp" : "";
-    if (staged) std::snprintf(h->variant_buf, sizeof(h->variant_buf), "smem-tma%s/ilp%d/W%u/Lc%dx%d", fmt, ilp, P.W, P.Lc, P.stages);
-    else std::snprintf(h->variant_buf, sizeof(h->variant_buf), "global%s/ilp%d/W%u", fmt, ilp, P.W);
+    char tn[16] = "";
+    if (P.TN != 32) std::snprintf(tn, sizeof(tn), "/tn%u", P.TN);
+    if (staged) std::snprintf(h->variant_buf, sizeof(h->variant_buf), "smem-tma%s/ilp%d/W%u/Lc%dx%d%s", fmt, ilp, P.W, P.Lc, P.stages, tn);
+    else std::snprintf(h->variant_buf, sizeof(h->variant_buf), "global%s/ilp%d/W%u%s", fmt, ilp, P.W, tn);
     h->last_variant = h->variant_buf;
 
     if (!metrics) {
+        if (h->fin_pending && !tail_reduces) return launch_finish(h); // many tiles: multi-block slot reduction (+ push)
         return NUFI_B200_OK; // rho_partial (and rho_full) are complete when the kernel ends, or the tail reduces the slots
     } else {
         finish_metrics_kernel<<<1, 32, 0, h->stream>>>(h->d_mpartials, grid, h->d_metrics);

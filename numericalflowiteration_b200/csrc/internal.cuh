@@ -38,8 +38,9 @@ struct BtParams
     unsigned long long Nvel_loc, vstride, voff; // this launch traces velocity nodes voff, voff+vstride, ... (Nvel_loc of them)
     unsigned long long l_first;      // first spatial node touched by [q_begin,q_end)
     unsigned long long l_last;       // last spatial node touched
-    unsigned int n_tiles;            // tiles of 32 consecutive nodes
-    unsigned int upt;                // warp-units per tile = ceil(Nvel / ILP)
+    unsigned int n_tiles;            // tiles of TN consecutive nodes
+    unsigned int TN, TNlog2;         // nodes per tile (32, 8, 4, 2 or 1): lane -> node lane % TN, velocity sub-index lane / TN
+    unsigned int upt;                // warp-units per tile = ceil(ceil(Nvel_loc / (32/TN)) / ILP)
     unsigned int W;                  // consumer warps per CTA
     unsigned int rpt;                // CTA-rounds per tile = ceil(upt / W)
     unsigned int R;                  // CTA-rounds in total = rpt * n_tiles
@@ -62,6 +63,7 @@ struct FinishParams
     double dV;
     unsigned long long l_first, l_last;
     unsigned int rpt, rpc, Tmax, n_tiles;
+    unsigned int TN;     // nodes per tile: node of (tile, lane) = l_first + tile*TN + lane, lanes >= TN carry zeros
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -210,6 +212,7 @@ struct Handle
     unsigned long long vstride = 1, voff = 0; // velocity share of the next backtrace launch (multi-GPU step), else 1, 0
     PeerState px;
     bool fin_push = false;       // the pending slot reduction also pushes to the peers (finish_push_kernel)
+    int tn_force = 0;            // nodes per tile forced by nufi_b200_set_tile_nodes (0: automatic)
     int variant_force = 0;
     const char *last_variant = "none";
     char variant_buf[64] = {0};

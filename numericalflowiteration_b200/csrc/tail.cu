@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
             double *ps = reinterpret_cast<double *>(part); // [8][N]
             for (int it = threadIdx.x; it < N * G; it += blockDim.x) {
                 const int l = it % N, g = it / N;
-                const unsigned tile = static_cast<unsigned>(l) >> 5, lane = l & 31;
+                const unsigned tile = static_cast<unsigned>(l) / F.TN, lane = static_cast<unsigned>(l) % F.TN;
                 const unsigned b_lo = (tile * F.rpt) / F.rpc, b_hi = ((tile + 1) * F.rpt - 1) / F.rpc;
                 for (int w = g; w < 8; w += G) ps[w * N + l] = slot_sum(tile, lane, b_lo, b_hi, w);
             }
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
             }
         } else {
             for (int l = threadIdx.x; l < N; l += blockDim.x) {
-                const unsigned tile = static_cast<unsigned>(l) >> 5, lane = l & 31;
+                const unsigned tile = static_cast<unsigned>(l) / F.TN, lane = static_cast<unsigned>(l) % F.TN;
                 const unsigned b_lo = (tile * F.rpt) / F.rpc, b_hi = ((tile + 1) * F.rpt - 1) / F.rpc;
                 double tot = 0;
 #pragma unroll

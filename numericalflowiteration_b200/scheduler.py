@@ -241,6 +241,10 @@ class CudaScheduler:
     def set_variant(self, v: int) -> None:
         self._ck(self._L.nufi_b200_set_variant(self._h, v))
 
+    def set_tile_nodes(self, nodes_per_tile: int) -> None:
+        """Lane layout of the backtrace kernel: 32 = one node per lane (default), 16..1 = 32/TN neighbouring velocities per node."""
+        self._ck(self._L.nufi_b200_set_tile_nodes(self._h, nodes_per_tile))
+
     def set_tail_variant(self, v: int) -> None:
         """0 auto, 1 cuFFT tail, 2 fused single-CTA tail."""
         self._ck(self._L.nufi_b200_set_tail_variant(self._h, v))

@@ -217,3 +217,35 @@ def test_fused_step_grid_sizes(shape, oracle):
     st = stride_t(conf)
     assert rel_linf(last, coeffs[(conf.Nt - 1) * st: conf.Nt * st]) <= 1e-8
     assert rel_linf(rho, oracle.rho(conf, f0, conf.Nt, coeffs)) <= 1e-9  # own (free-running) history vs oracle history
+
+
+@pytest.mark.parametrize("tn", [16, 8, 4, 1])
+@pytest.mark.parametrize("name", ["1d-two-stream", "2d-landau", "3d-landau", "3d-bump"])
+def test_tile_nodes_lane_layouts(name, tn, histories, oracle):
+    """Every lane layout (nodes per tile 32 ... 1: 32/TN lanes per node with neighbouring velocities, combined by a shuffle
+    tree before the slot is written) gives the reference's rho: whole range, a ragged q-range, the fused step and the
+    peer-exchange path with a world of one."""
+    conf, f0, coeffs, energy = histories[name]
+    n = conf.Nt - 1
+    want = oracle.rho(conf, f0, n, coeffs)
+    with CudaScheduler(conf, f0, device=0) as s:
+        s.set_tile_nodes(tn)
+        s.upload_history(coeffs, n)
+        got = s.eval_rho(n)
+        assert f"/tn{tn}" in s.last_variant
+        assert rel_linf(got, want) <= RHO_TOL
+        nq = s.n_quad
+        q0, q1 = nq // 3 + 5, (2 * nq) // 3 + 1
+        part = np.zeros(s.n_nodes)
+        s.compute_rho(n, q0, q1)
+        s.download_rho(part)
+        ref_part = oracle.rho_partial(conf, f0, n, coeffs, q0, q1)
+        assert np.max(np.abs(part - ref_part)) <= RHO_TOL * np.max(np.abs(want))
+        s.step(n)
+        e = s.download_energy(n, n + 1)[0]
+        assert abs(e - energy[n]) <= 1e-8 * abs(energy[n])
+        s.peer_attach(0, 1, s.peer_export(1))
+        s.peer_step(n)
+        e2 = s.download_energy(n, n + 1)[0]
+        assert abs(e2 - e) <= 1e-12 * abs(e)
+        assert not s.peer_timed_out()

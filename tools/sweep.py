@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--W", type=int, nargs="*", default=[0])
     ap.add_argument("--lc", type=int, nargs="*", default=[0])
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--tn", type=int, nargs="*", default=[0], help="nodes per tile (NUFI_B200_TN): 32, 16, 8, 4, 2, 1")
     ap.add_argument("--xpp", type=int, default=-1, help="level format of 2d/3d histories: 0 B-spline, 1 xpp, -1 auto")
     a = ap.parse_args()
     conf, f0, depth, desc = make_workload(a.workload, 1)
@@ -36,8 +37,8 @@ def main():
     r.s.set_kernel_timing(True)
     ps = float(n_quad(conf)) * n
     print(desc, "depth", n, flush=True)
-    for ilp, W, lc in itertools.product(a.ilp, a.W, a.lc):
-        for k, v in (("NUFI_B200_ILP", ilp), ("NUFI_B200_W", W), ("NUFI_B200_LC", lc)):
+    for ilp, W, lc, tn in itertools.product(a.ilp, a.W, a.lc, a.tn):
+        for k, v in (("NUFI_B200_ILP", ilp), ("NUFI_B200_W", W), ("NUFI_B200_LC", lc), ("NUFI_B200_TN", tn)):
             if v:
                 os.environ[k] = str(v)
             else:
@@ -51,7 +52,7 @@ def main():
                 r.s.compute_rho(n, 0, r.s.n_quad)
             ms, cnt = r.s.backtrace_time(reset=True)
             ms /= cnt
-            print(f"ilp={ilp} W={W} lc={lc}: {r.s.last_variant:28s} {ms:9.4f} ms  {ps / ms / 1e6:8.2f} Gps/s  "
+            print(f"ilp={ilp} W={W} lc={lc} tn={tn}: {r.s.last_variant:34s} {ms:9.4f} ms  {ps / ms / 1e6:8.2f} Gps/s  "
                   f"{ps * FLOP_PER_POINT_STEP[conf.dim] / ms / 1e9:6.2f} TF", flush=True)
         except Exception as e:  # noqa: BLE001
             print(f"ilp={ilp} W={W} lc={lc}: {e}", flush=True)
