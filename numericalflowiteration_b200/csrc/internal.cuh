@@ -104,18 +104,19 @@ struct PeerRecv // receiver side (tail_small_kernel / peer_gather_kernel)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// Receiver: thread r < world spins (bounded, ~2 s) until rank r's flag of this epoch has arrived.  Call from all threads
+// Receiver: thread r < world spins (bounded, ~17 s; not at all once a wait has already given up) until rank r's flag of this epoch has arrived.  Call from all threads
 // of the block and follow with __syncthreads(); read the data with __ldcg (L2: the peers wrote it behind L1's back).
 __device__ __forceinline__ void peer_wait_all(const PeerRecv &X)
 {
     if (static_cast<int>(threadIdx.x) < X.world) {
         const unsigned long long *f = X.flags + threadIdx.x;
         const long long t0 = clock64();
+        const bool gave_up_before = *reinterpret_cast<volatile int *>(X.status) != 0; // sticky: later steps do not wait again
         for (;;) {
             unsigned long long v;
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-            if (v >= X.epoch) break;
-            if (clock64() - t0 > (1ll << 32)) { // a peer never pushed: do not hang the GPU, report through the status word
+            if (v >= X.epoch || gave_up_before) break;
+            if (clock64() - t0 > (1ll << 35)) { // a peer never pushed: do not hang the GPU, report through the status word
                 *X.status = 1;
                 break;
             }
