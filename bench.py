@@ -67,7 +67,7 @@ class ClockSampler:
     BAD = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80}
     NOTE = {"sw_power_cap": 0x4}
 
-    def __init__(self, index: int, period_s: float = 0.02):
+    def __init__(self, index: int, period_s: float = 0.004):
         self.samples, self.reasons, self.sm_max, self.ok = [], set(), None, False
         self.period = period_s
         self._stop = threading.Event()
