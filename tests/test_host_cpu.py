@@ -239,3 +239,35 @@ int main(int argc, char** argv){
     assert [int(x) for x in out] == [3, 4, 4, st]
     assert open(tmp_path / "h2.bin", "rb").read() == open(tmp_path / "h.bin", "rb").read()
     assert np.array_equal(history_io.read_text(tmp_path / "h2.txt", 4 * st, header_lines=7), coeffs)
+
+
+def test_c_abi_header_is_plain_c(tmp_path):
+    """include/nufi_b200.h is the drop-in boundary: plain C (C99, -pedantic clean), no C++ or torch types in any signature."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "nufi_b200.h"\nint main(void) { nufi_b200_config3d c; (void)c; return NUFI_B200_PEER_HANDLE_BYTES == 64 ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c", str(src),
+                        "-o", str(tmp_path / "hdr.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "nufi_b200.h")).read(), flags=re.S)  # declarations only
+    assert "torch" not in hdr and "std::" not in hdr and "at::" not in hdr and "&" not in hdr
+
+
+def test_fullsize_fixtures_are_consistent():
+    """The committed full-size reference traces (tests/golden/fullsize_*.npz) belong to bench.py's workloads, start at the closed-form
+    step-0 energy and, where both of the reference's builds were run, agree with each other while the problem is well conditioned."""
+    import numpy as np
+
+    sys.path.insert(0, ROOT)
+    from bench import make_workload
+
+    gold = os.path.join(ROOT, "tests", "golden")
+    for name in ("C1", "C2", "C3", "C4"):
+        g = np.load(os.path.join(gold, f"fullsize_{name}.npz"))
+        conf, f0, _, desc = make_workload(name, 1)
+        assert str(g["workload"]) == desc and int(g["f0_kind"]) == f0.kind and list(g["f0_p"]) == list(f0.p)
+        assert len(g["energy"]) == int(g["steps"]) and np.all(np.isfinite(g["energy"])) and np.all(g["energy"] > 0)
+    for name in ("C1", "C2"):  # 1d, alpha = 0.01, k = 0.5, L = 4 pi: E_0 = L alpha^2 / (4 k^2) = 4 pi * 1e-4
+        a = np.load(os.path.join(gold, f"fullsize_{name}.npz"))["energy"]
+        b = np.load(os.path.join(gold, f"fullsize_{name}_canonical.npz"))["energy"]
+        assert abs(a[0] - 4 * np.pi * 1e-4) <= 1e-12 * a[0] and abs(b[0] - a[0]) <= 1e-12 * a[0]
+        assert np.max(np.abs(a[:300] - b[:300]) / a[:300]) <= 1e-9  # -O3/FMA vs -O2 builds of the reference, first 300 steps
