@@ -13,6 +13,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 namespace nufi_b200
 {
@@ -391,7 +392,7 @@ __device__ __forceinline__ void transform_dim(double2 *&cur, double2 *&oth, doub
 __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __grid_constant__ SmallTailParams S)
 {
 #ifdef NUFI_TAIL_TIMING
-    __shared__ long long tmark[8];
+    __shared__ long long tmark[24];
 #endif
     TAIL_MARK(0);
     extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -412,7 +413,23 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
         ilx[i] = T.ilx[i];
         kap2x[i] = T.kap2x[i];
     }
+    // slot bookkeeping without integer divisions in the load loops: first tile of every backtrace CTA and the CTA range of every
+    // tile, tabulated here (one division per thread, hidden behind the backtrace kernel by the programmatic launch)
+    __shared__ unsigned short s_tfirst[256], s_blo[128], s_bhi[128];
+    const bool tabulated = !S.rho && !S.X.world && S.F.n_tiles <= 128 && S.F.rpc > 0 && (S.F.rpt * S.F.n_tiles + S.F.rpc - 1) / S.F.rpc <= 256;
+    if (tabulated) {
+        const FinishParams &F = S.F;
+        const unsigned n_ctas = (F.rpt * F.n_tiles + F.rpc - 1) / F.rpc;
+        for (unsigned b = threadIdx.x; b < n_ctas; b += blockDim.x) s_tfirst[b] = static_cast<unsigned short>((b * F.rpc) / F.rpt);
+        for (unsigned t = threadIdx.x; t < F.n_tiles; t += blockDim.x) {
+            s_blo[t] = static_cast<unsigned short>((t * F.rpt) / F.rpc);
+            s_bhi[t] = static_cast<unsigned short>(((t + 1) * F.rpt - 1) / F.rpc);
+        }
+    }
+    TAIL_MARK(8);
     pdl_wait(); // everything below reads what the kernels ahead of this one on the stream wrote
+    __syncthreads(); // the slot tables above are complete
+    TAIL_MARK(9);
     // ---- rho (either given, or the fixed-order sum of the backtrace kernel's per-(CTA, tile) slots: per node 8 strided
     //      partial sums over the CTAs that touched its tile, then added in order -- the association of finish_rho_kernel)
     if (S.rho) {
@@ -434,8 +451,12 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
 #pragma unroll
                 for (unsigned u = 0; u < 4; ++u) {
                     const unsigned bb = b + 8 * u;
-                    const unsigned t_first = (bb * F.rpc) / F.rpt;
-                    v[u] = bb <= b_hi ? F.slots[(static_cast<size_t>(bb) * F.Tmax + (tile - t_first)) * 32 + lane] : 0.0;
+                    if (bb <= b_hi) {
+                        const unsigned t_first = tabulated ? s_tfirst[bb] : (bb * F.rpc) / F.rpt;
+                        v[u] = F.slots[(static_cast<size_t>(bb) * F.Tmax + (tile - t_first)) * 32 + lane];
+                    } else {
+                        v[u] = 0.0;
+                    }
                 }
                 sum = (((sum + v[0]) + v[1]) + v[2]) + v[3];
             }
@@ -451,13 +472,17 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
             int G = 1;                 // threads per node
             while (2 * G * N <= static_cast<int>(blockDim.x) && G < 8) G *= 2;
             double *ps = reinterpret_cast<double *>(part); // [8][N]
+            const unsigned tn_log2 = 31 - __clz(F.TN); // TN is a power of two
             for (int it = threadIdx.x; it < N * G; it += blockDim.x) {
-                const int l = it % N, g = it / N;
-                const unsigned tile = static_cast<unsigned>(l) / F.TN, lane = static_cast<unsigned>(l) % F.TN;
-                const unsigned b_lo = (tile * F.rpt) / F.rpc, b_hi = ((tile + 1) * F.rpt - 1) / F.rpc;
+                int l = it, g = 0;
+                while (l >= N) { l -= N; ++g; } // g < G <= 8
+                const unsigned tile = static_cast<unsigned>(l) >> tn_log2, lane = static_cast<unsigned>(l) & (F.TN - 1);
+                const unsigned b_lo = tabulated ? s_blo[tile] : (tile * F.rpt) / F.rpc;
+                const unsigned b_hi = tabulated ? s_bhi[tile] : ((tile + 1) * F.rpt - 1) / F.rpc;
                 for (int w = g; w < 8; w += G) ps[w * N + l] = slot_sum(tile, lane, b_lo, b_hi, w);
             }
             __syncthreads();
+            TAIL_MARK(10);
             for (int l = threadIdx.x; l < N; l += blockDim.x) {
                 double tot = 0;
 #pragma unroll
@@ -465,9 +490,11 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
                 store_rho(l, tot);
             }
         } else {
+            const unsigned tn_log2 = 31 - __clz(F.TN);
             for (int l = threadIdx.x; l < N; l += blockDim.x) {
-                const unsigned tile = static_cast<unsigned>(l) / F.TN, lane = static_cast<unsigned>(l) % F.TN;
-                const unsigned b_lo = (tile * F.rpt) / F.rpc, b_hi = ((tile + 1) * F.rpt - 1) / F.rpc;
+                const unsigned tile = static_cast<unsigned>(l) >> tn_log2, lane = static_cast<unsigned>(l) & (F.TN - 1);
+                const unsigned b_lo = tabulated ? s_blo[tile] : (tile * F.rpt) / F.rpc;
+                const unsigned b_hi = tabulated ? s_bhi[tile] : ((tile + 1) * F.rpt - 1) / F.rpc;
                 double tot = 0;
 #pragma unroll
                 for (int w = 0; w < 8; ++w) tot += slot_sum(tile, lane, b_lo, b_hi, w);
@@ -556,7 +583,8 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
 #ifdef NUFI_TAIL_TIMING
     TAIL_MARK(5);
     if (threadIdx.x == 0)
-        printf("tail phases (cycles): rho+tw %lld  fwd %lld  symbol %lld  inv %lld  expand %lld  total %lld\n", tmark[1] - tmark[0],
+        printf("tail phases (cycles): rho+tw %lld [tables %lld, pdl_wait %lld, slot loads %lld, combine %lld]  fwd %lld  symbol %lld  inv %lld  expand %lld  total %lld\n",
+               tmark[1] - tmark[0], tmark[8] - tmark[0], tmark[9] - tmark[8], tmark[10] - tmark[9], tmark[1] - tmark[10],
                tmark[2] - tmark[1], tmark[3] - tmark[2], tmark[4] - tmark[3], tmark[5] - tmark[4], tmark[5] - tmark[0]);
 #endif
 }
@@ -718,7 +746,12 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full, bool from_peer)
         const size_t smem = (2 * h->n_nodes + 2 * (c.Nx + c.Ny + c.Nz) + kSmallPart) * sizeof(double2) + ((c.Nx + c.Ny + c.Nz + 1) & ~size_t(1)) * sizeof(double);
         if (smem > 48 * 1024)
             NUFI_CUDA_CHECK(h, cudaFuncSetAttribute(tail_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        NUFI_CUDA_CHECK(h, launch_chained(h, tail_small_kernel, dim3(1), dim3(kSmallThreads), smem, S));
+        unsigned threads = kSmallThreads;
+        if (const char *e = std::getenv("NUFI_B200_TAIL_THREADS")) { // experiments: every loop of the kernel strides by blockDim
+            const int v = std::atoi(e);
+            if (v >= 32 && v <= kSmallThreads && v % 32 == 0) threads = static_cast<unsigned>(v);
+        }
+        NUFI_CUDA_CHECK(h, launch_chained(h, tail_small_kernel, dim3(1), dim3(threads), smem, S));
         h->launches += 1;
         h->last_tail = "fused-1cta";
         h->level_valid[n] = 1;
