@@ -338,32 +338,60 @@ __device__ __forceinline__ void dft_pass(const double2 *A, double2 *B, double2 *
     }
 }
 
-// Radix-2 Stockham FFT along a power-of-two dimension, all lines of the grid at once (N/2 butterflies per stage, ping-pong
-// between the two buffers, twiddles from the exact table).  Returns with the result in `cur` (pointers swapped as needed).
+// u * exp(SIGN * i * angle), w = (cos, sin)(angle)
+template <int SIGN> __device__ __forceinline__ double2 cmul_tw(double2 u, double2 w)
+{
+    if (SIGN < 0) return make_double2(fma(u.x, w.x, u.y * w.y), fma(u.y, w.x, -u.x * w.y));
+    return make_double2(fma(u.x, w.x, -u.y * w.y), fma(u.y, w.x, u.x * w.y));
+}
+
+// Stockham FFT along a power-of-two dimension, all lines of the grid at once, ping-pong between the two buffers, twiddles from
+// the exact table: one radix-2 stage if log2(Nd) is odd, then radix-4 stages (N/4 butterflies each) -- half the stages and
+// block-wide barriers of a pure radix-2 scheme; the tail is latency-bound, not work-bound.  Returns with the result in `cur`.
 template <int SIGN>
 __device__ __forceinline__ void fft_pass(double2 *&cur, double2 *&oth, int N, int Nd, int stride, const double2 *tw)
 {
-    const int half = Nd >> 1;
-    const int lh = 31 - __clz(half); // log2(half)
-    int ls = 0;                      // log2(Ns)
-    for (int Ns = 1; Ns < Nd; Ns <<= 1, ++ls) {
-        const int tshift = lh - ls;  // twiddle index step = Nd / (2 Ns)
+    const int lg = 31 - __clz(Nd);
+    int Ns = 1, ls = 0; // current sub-transform length and its log2
+    if (lg & 1) {       // radix-2 stage with Ns = 1: all twiddles are 1
+        const int half = Nd >> 1, lh = lg - 1;
         for (int t = threadIdx.x; t < (N >> 1); t += blockDim.x) {
             int lo = 0, q = t;
             if (stride != 1) { q = t / stride; lo = t - q * stride; }
             const int j = q & (half - 1);
-            const int hi = q >> lh;
-            const int base = hi * stride * Nd + lo;
-            const int kk = j & (Ns - 1);
+            const int base = (q >> lh) * stride * Nd + lo;
             const double2 v0 = cur[base + j * stride];
-            const double2 u = cur[base + (j + half) * stride];
-            const double2 w = tw[kk << tshift];
-            double2 v1; // u * exp(SIGN * i * angle)
-            if (SIGN < 0) v1 = make_double2(fma(u.x, w.x, u.y * w.y), fma(u.y, w.x, -u.x * w.y));
-            else v1 = make_double2(fma(u.x, w.x, -u.y * w.y), fma(u.y, w.x, u.x * w.y));
-            const int d = ((j >> ls) << (ls + 1)) + kk;
-            oth[base + d * stride] = make_double2(v0.x + v1.x, v0.y + v1.y);
-            oth[base + (d + Ns) * stride] = make_double2(v0.x - v1.x, v0.y - v1.y);
+            const double2 v1 = cur[base + (j + half) * stride];
+            oth[base + (2 * j) * stride] = make_double2(v0.x + v1.x, v0.y + v1.y);
+            oth[base + (2 * j + 1) * stride] = make_double2(v0.x - v1.x, v0.y - v1.y);
+        }
+        __syncthreads();
+        double2 *tmp = cur; cur = oth; oth = tmp;
+        Ns = 2; ls = 1;
+    }
+    const int quarter = Nd >> 2, lq = lg - 2;
+    for (; Ns < Nd; Ns <<= 2, ls += 2) {
+        const int tshift = lq - ls; // twiddle index step = Nd / (4 Ns)
+        for (int t = threadIdx.x; t < (N >> 2); t += blockDim.x) {
+            int lo = 0, q = t;
+            if (stride != 1) { q = t / stride; lo = t - q * stride; }
+            const int j = q & (quarter - 1);
+            const int base = (q >> lq) * stride * Nd + lo;
+            const int k = j & (Ns - 1);
+            const int m = k << tshift;
+            const double2 v0 = cur[base + j * stride];
+            const double2 v1 = cmul_tw<SIGN>(cur[base + (j + quarter) * stride], tw[m]);
+            const double2 v2 = cmul_tw<SIGN>(cur[base + (j + 2 * quarter) * stride], tw[2 * m]);
+            const double2 v3 = cmul_tw<SIGN>(cur[base + (j + 3 * quarter) * stride], tw[3 * m]);
+            const double2 a = make_double2(v0.x + v2.x, v0.y + v2.y), b = make_double2(v0.x - v2.x, v0.y - v2.y);
+            const double2 c = make_double2(v1.x + v3.x, v1.y + v3.y), d = make_double2(v1.x - v3.x, v1.y - v3.y);
+            // i * d = (-d.y, d.x); forward (SIGN < 0): y1 = b - i d, y3 = b + i d; inverse: the other way round
+            const double2 id = SIGN < 0 ? make_double2(d.y, -d.x) : make_double2(-d.y, d.x);
+            const int o = (((j >> ls) << (ls + 2)) + k) * stride + base;
+            oth[o] = make_double2(a.x + c.x, a.y + c.y);
+            oth[o + Ns * stride] = make_double2(b.x + id.x, b.y + id.y);
+            oth[o + 2 * Ns * stride] = make_double2(a.x - c.x, a.y - c.y);
+            oth[o + 3 * Ns * stride] = make_double2(b.x - id.x, b.y - id.y);
         }
         __syncthreads();
         double2 *tmp = cur; cur = oth; oth = tmp;
