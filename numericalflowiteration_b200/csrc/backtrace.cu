@@ -414,7 +414,11 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1)
     backtrace_kernel(const __grid_constant__ BtParams P, const __grid_constant__ EpilogueParams E)
 {
     __shared__ unsigned int s_ticket;
+    __shared__ unsigned short s_tfirst[256]; // epilogue: first tile of every CTA (filled below, read by the last CTA only)
     pdl_trigger(); // the slot reduction / field tail behind this launch may be scheduled as soon as an SM has room
+    if (E.mode) // visible to the epilogue through the CTA's barriers (the producer warp's share through the __syncthreads below)
+        for (unsigned b = threadIdx.x; b < E.n_active && b < 256; b += blockDim.x)
+            s_tfirst[b] = static_cast<unsigned short>((b * E.F.rpc) / E.F.rpt);
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);
     unsigned long long *empty = full + kMaxStages;
@@ -674,8 +678,11 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP>::max_threads, 1)
 #pragma unroll
                                 for (unsigned u = 0; u < 4; ++u) {
                                     const unsigned bb = b + 8 * u;
-                                    const unsigned t_first = (bb * F.rpc) / F.rpt;
-                                    v[u] = bb <= b_hi ? __ldcg(F.slots + (static_cast<size_t>(bb) * F.Tmax + (tile - t_first)) * 32 + lane) : 0.0;
+                                    v[u] = 0.0;
+                                    if (bb <= b_hi) { // first tile of CTA bb: tabulated at kernel start (no division per load)
+                                        const unsigned t_first = bb < 256 ? s_tfirst[bb] : (bb * F.rpc) / F.rpt;
+                                        v[u] = __ldcg(F.slots + (static_cast<size_t>(bb) * F.Tmax + (tile - t_first)) * 32 + lane);
+                                    }
                                 }
                                 sum = (((sum + v[0]) + v[1]) + v[2]) + v[3]; // + 0.0 is exact: same order as one-by-one
                             }
