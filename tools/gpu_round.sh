@@ -17,5 +17,6 @@ ncu -i gpurun_out/prof_$1.ncu-rep --page raw --csv 2>/dev/null | gzip > gpurun_o
 ncu -i gpurun_out/prof_$1.ncu-rep --page source --csv 2>/dev/null | gzip > gpurun_out/src_$1.csv.gz
 rm -f gpurun_out/prof_$1.ncu-rep
 done
+[ -x tools/build/microbench ] || { mkdir -p tools/build; nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/build/microbench tools/microbench.cu; }
 ./tools/build/microbench > gpurun_out/microbench.txt 2>&1
 ls -la gpurun_out
