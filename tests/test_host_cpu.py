@@ -271,3 +271,23 @@ def test_fullsize_fixtures_are_consistent():
         b = np.load(os.path.join(gold, f"fullsize_{name}_canonical.npz"))["energy"]
         assert abs(a[0] - 4 * np.pi * 1e-4) <= 1e-12 * a[0] and abs(b[0] - a[0]) <= 1e-12 * a[0]
         assert np.max(np.abs(a[:300] - b[:300]) / a[:300]) <= 1e-9  # -O3/FMA vs -O2 builds of the reference, first 300 steps
+
+
+def test_bench_reference_arm_line_contract():
+    """`bench.py --impl reference` (the reference's own CPU eval_rho on the host cores) prints ONE JSON line with the keys the
+    driver reads; it runs without a GPU."""
+    import json
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C4", "--steps", "1",
+                        "--warmup", "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "backtrace point-steps/sec" and d["unit"] == "point-steps/s"
+    for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config"):
+        assert k in d
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["dtype"] == "f64" and "workload" in d["config"]
+    cb, e2e = d["cpu_baseline"], d["e2e"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert e2e["value"] == d["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
