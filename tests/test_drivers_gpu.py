@@ -214,3 +214,27 @@ def test_torchrun_peer_exchange_ipc(tmp_path):
                         "--master-port", "29571", str(script)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+
+
+def test_bench_line_contract():
+    """`python bench.py` prints ONE JSON line with the keys the driver reads (value, e2e, roofline, cpu_baseline, gpu_launches,
+    clocks), measured through the C ABI on this GPU; the live parity check inside it must be within tolerance."""
+    import json
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "C4", "--steps", "5", "--warmup", "3", "--no-extras",
+                        "--cpu-budget", "0.5"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["metric"] == "backtrace point-steps/sec" and d["unit"] == "point-steps/s" and d["n_gpus"] == 1 and d["dtype"] == "f64"
+    assert d["value"] > 0 and d["gpu_launches"] >= 2 * d["steps"] and d["scaling"] == "weak" and d["vs_baseline"] is None
+    roof = d["roofline"]
+    assert roof["bound"] == "fp64" and 0 < roof["frac"] < 1.5 and roof["unit"] == "TFLOP/s" and roof["kernel_ms"] > 0
+    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12 and 0 < roof["smem"]["frac"] < 1
+    e2e = d["e2e"]
+    assert 0 < e2e["value"] <= d["value"] * 1.05 and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] > 0
+    assert d["parity"]["rho_rel_linf_vs_cpu_reference"] <= d["parity"]["tolerance"] == 1e-10
+    assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"]
