@@ -291,3 +291,45 @@ def test_bench_reference_arm_line_contract():
     cb, e2e = d["cpu_baseline"], d["e2e"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert e2e["value"] == d["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+
+
+def test_radix4_stockham_index_scheme():
+    """numpy restatement of the index arithmetic of csrc/tail.cu: fft_pass (one radix-2 stage when log2(Nd) is odd, then radix-4
+    Stockham stages, twiddle index r*k*Nd/(4 Ns), output index ((j >> ls) << (ls+2)) + k + r*Ns) against numpy's FFT -- the scheme
+    was validated this way on the CPU before the kernel ran on the GPU (where tests/test_gpu_parity.py::test_field_tail checks it)."""
+    import numpy as np
+
+    def fft_pass(x, sign):
+        nd = len(x)
+        lg = nd.bit_length() - 1
+        tw = np.exp(2j * np.pi * np.arange(nd) / nd)
+
+        def ctw(u, w):
+            return u * (np.conj(w) if sign < 0 else w)
+
+        cur, oth = x.astype(complex).copy(), np.zeros(nd, complex)
+        ns, ls = 1, 0
+        if lg & 1:
+            half = nd >> 1
+            for j in range(half):
+                oth[2 * j], oth[2 * j + 1] = cur[j] + cur[j + half], cur[j] - cur[j + half]
+            cur, oth, ns, ls = oth, cur, 2, 1
+        quarter, lq = nd >> 2, lg - 2
+        while ns < nd:
+            tshift = lq - ls
+            for j in range(quarter):
+                k = j & (ns - 1)
+                m = k << tshift
+                v0, v1, v2, v3 = cur[j], ctw(cur[j + quarter], tw[m]), ctw(cur[j + 2 * quarter], tw[2 * m]), ctw(cur[j + 3 * quarter], tw[3 * m])
+                a, b, c, d = v0 + v2, v0 - v2, v1 + v3, v1 - v3
+                idd = -1j * d if sign < 0 else 1j * d
+                o = ((j >> ls) << (ls + 2)) + k
+                oth[o], oth[o + ns], oth[o + 2 * ns], oth[o + 3 * ns] = a + c, b + idd, a - c, b - idd
+            cur, oth, ns, ls = oth, cur, ns << 2, ls + 2
+        return cur
+
+    rng = np.random.default_rng(1)
+    for nd in (8, 16, 32, 64, 128, 256):
+        x = rng.normal(size=nd) + 1j * rng.normal(size=nd)
+        assert np.max(np.abs(fft_pass(x, -1) - np.fft.fft(x))) <= 1e-12
+        assert np.max(np.abs(fft_pass(x, +1) - np.fft.ifft(x) * nd)) <= 1e-12
