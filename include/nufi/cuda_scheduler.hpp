@@ -90,6 +90,7 @@ public:
     double solve_interpolate(size_t n) { double e = 0; ck(nufi_b200_solve_interpolate(h_, n, &e)); return e; }
     double electric_energy(size_t n) { double e = 0; ck(nufi_b200_download_energy(h_, n, n + 1, &e)); return e; }
     void download_phi(size_t n, double *level) { ck(nufi_b200_download_phi(h_, n, level)); }
+    void eval_phase_flow(size_t n, size_t npts, const double *points, double *feet) { ck(nufi_b200_eval_phase_flow(h_, n, npts, points, feet)); }
     void sync() { ck(nufi_b200_sync(h_)); }
     nufi_b200_handle *handle() const noexcept { return h_; }
     const Conf &config() const noexcept { return conf_; }

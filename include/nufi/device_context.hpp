@@ -54,6 +54,14 @@ public:
         return cache;
     }
 
+    // feet (x.., v..) at t = 0 of the characteristics through `npts` phase-space points at t_n (needs levels 0..n of coeffs)
+    void phase_flow(size_t n, size_t npts, const double *points, double *feet, const double *coeffs)
+    {
+        std::lock_guard<std::mutex> lock(mtx);
+        if (n > 1) sync_levels(n + 1, coeffs);
+        kern.eval_phase_flow(n, npts, points, feet);
+    }
+
     kernel_impl<Conf, order> &kernel() { return kern; }
 
 private:

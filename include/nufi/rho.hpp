@@ -29,6 +29,26 @@ namespace nufi
     }                                                                                                                   \
     }
 
+// eval_phase_flow (nufi/rho.hpp:98-131; dim1 in the reference, bin/test_nufi_gpu_1d.cpp:155,190,339): the reference's
+// signature (one point per call, x and u updated in place -- one device call per point) and a batched form for plot grids.
+namespace dim1
+{
+template <typename real, size_t order> void eval_phase_flow(size_t n, real &x, real &u, const real *coeffs, const config_t<real> &conf)
+{
+    static_assert(std::is_same<real, double>::value, "libnufi_b200 computes in FP64");
+    double in[2] = {x, u}, out[2];
+    detail::context<config_t<real>, order>(conf).phase_flow(n, 1, in, out, coeffs);
+    x = out[0];
+    u = out[1];
+}
+template <typename real, size_t order>
+void eval_phase_flow_all(size_t n, size_t npts, const real *points /*[npts][2]: x, u*/, real *feet, const real *coeffs, const config_t<real> &conf)
+{
+    static_assert(std::is_same<real, double>::value, "libnufi_b200 computes in FP64");
+    detail::context<config_t<real>, order>(conf).phase_flow(n, npts, points, feet, coeffs);
+}
+} // namespace dim1
+
 NUFI_B200_DEFINE_RHO(dim1)
 NUFI_B200_DEFINE_RHO(dim2)
 NUFI_B200_DEFINE_RHO(dim3)

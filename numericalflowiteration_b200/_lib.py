@@ -24,7 +24,7 @@ SYMBOLS = [
     "nufi_b200_group_create", "nufi_b200_group_destroy", "nufi_b200_group_step", "nufi_b200_group_sync",
     "nufi_b200_group_last_error", "nufi_b200_device_count", "nufi_b200_device_of",
     "nufi_b200_peer_export", "nufi_b200_peer_attach", "nufi_b200_peer_step", "nufi_b200_peer_status", "nufi_b200_peer_detach",
-    "nufi_b200_group_set_exchange", "nufi_b200_group_exchange", "nufi_b200_set_kernel_timing", "nufi_b200_set_tile_nodes",
+    "nufi_b200_group_set_exchange", "nufi_b200_group_exchange", "nufi_b200_set_kernel_timing", "nufi_b200_set_tile_nodes", "nufi_b200_eval_phase_flow",
 ]
 
 _lib = None
@@ -64,7 +64,7 @@ def load() -> C.CDLL:
         "set_variant": [vp, i], "measure_fp64_peak": [i, dp], "set_kernel_timing": [vp, i], "set_tile_nodes": [vp, i],
         "backtrace_time": [vp, dp, C.POINTER(C.c_uint64), i], "set_tail_variant": [vp, i],
         "download_history": [vp, sz, vp], "upload_history": [vp, sz, vp], "eval_f": [vp, sz, sz, vp, vp, i],
-        "eval_field": [vp, sz, i, sz, vp, vp],
+        "eval_field": [vp, sz, i, sz, vp, vp], "eval_phase_flow": [vp, sz, sz, vp, vp],
         "poisson_solve": [vp, vp, dp], "interpolate": [vp, vp, vp], "device_count": [C.POINTER(i)], "device_of": [vp],
         "group_create": [C.POINTER(vp), i, C.POINTER(vp)], "group_step": [vp, sz], "group_sync": [vp],
         "group_set_exchange": [vp, i],

@@ -499,6 +499,27 @@ int nufi_b200_eval_f(nufi_b200_handle *h, size_t n, size_t npts, const double *p
     return NUFI_B200_OK;
 }
 
+int nufi_b200_eval_phase_flow(nufi_b200_handle *h, size_t n, size_t npts, const double *points_host, double *feet_host)
+{
+    ENTER(h);
+    if (n > hh->Nt) return fail(hh, NUFI_B200_ERR_RANGE, "Time-step out of range.");
+    if (npts == 0) return NUFI_B200_OK;
+    if (!points_host || !feet_host) return fail(hh, NUFI_B200_ERR_ARG, "points / feet is NULL");
+    const bool traced = n > 1; // the reference traces nothing for n <= 1 (nufi/rho.hpp:102) and only reduces x into the box
+    int rc = check_levels(hh, traced ? n + 1 : 0, "eval_phase_flow");
+    if (rc) return rc;
+    const size_t w = 2 * static_cast<size_t>(hh->dim);
+    DeviceScratch d;
+    if (cudaMalloc(&d.p, sizeof(double) * npts * 2 * w) != cudaSuccess) return fail(hh, NUFI_B200_ERR_ALLOC, "cudaMalloc of the sample points failed");
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(d.p, points_host, sizeof(double) * npts * w, cudaMemcpyHostToDevice, hh->stream));
+    // n <= 1: the kernel runs with no level to read (n = 0, eval_ftilda form) and just locates / re-assembles the point
+    rc = launch_sample_f(hh, traced ? n : 0, npts, d.p, d.p + npts * w, /*full=*/traced, /*feet=*/true);
+    if (rc) return rc;
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(feet_host, d.p + npts * w, sizeof(double) * npts * w, cudaMemcpyDeviceToHost, hh->stream));
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    return NUFI_B200_OK;
+}
+
 int nufi_b200_eval_field(nufi_b200_handle *h, size_t n, int derivative_axis, size_t npts, const double *points_host, double *values_host)
 {
     ENTER(h);

@@ -840,6 +840,7 @@ struct SampleParams
     double *out;
     size_t npts;
     int with_first_half_kick; // 1: eval_f (nufi/rho.hpp:63-96, 234-281, 369-426), 0: eval_ftilda
+    int feet;                 // 1: write the foot (x.., v..) of the characteristic instead of f0 there (eval_phase_flow, rho.hpp:98-131)
 };
 
 // f(t_n, x, v) at arbitrary phase-space points: one thread per point, history read from global memory.
@@ -856,6 +857,21 @@ template <int DIM, bool XPP> __global__ void sample_f_kernel(const __grid_consta
         for (int d = 0; d < DIM; ++d) p.vel[d] = q[DIM + d];
         if (P.first_level >= 0) slow_trace<DIM, XPP>(p, P); // robust path: true modulo wrap, any jump length
         const double x = P.x_min + (p.cell[0] + (0.5 + p.tau[0])) * P.dx;
+        if (S.feet) { // the flow map itself; positions reduced with L*floor(x*L_inv) as the reference does (no x_min shift)
+            double *o = S.out + i * 2 * DIM;
+            o[0] = x - S.Lx * floor(x * S.Lx_inv);
+            if constexpr (DIM >= 2) {
+                const double y = P.y_min + (p.cell[1] + (0.5 + p.tau[1])) * P.dy;
+                o[1] = y - S.Ly * floor(y * S.Ly_inv);
+            }
+            if constexpr (DIM >= 3) {
+                const double z = P.z_min + (p.cell[2] + (0.5 + p.tau[2])) * P.dz;
+                o[2] = z - S.Lz * floor(z * S.Lz_inv);
+            }
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) o[DIM + d] = p.vel[d];
+            continue;
+        }
         double f;
         if constexpr (DIM == 1) f = f0_1d(P, x, p.vel[0]);
         else if constexpr (DIM == 2) f = f0_2d(P, x, P.y_min + (p.cell[1] + (0.5 + p.tau[1])) * P.dy, p.vel[0], p.vel[1]);
@@ -1200,9 +1216,10 @@ static void fill_common(const Handle *h, BtParams &P)
     for (int i = 0; i < 4; ++i) P.f0p[i] = h->f0.p[i];
 }
 
-int launch_sample_f(Handle *h, size_t n, size_t npts, const double *d_pts, double *d_out, bool full)
+int launch_sample_f(Handle *h, size_t n, size_t npts, const double *d_pts, double *d_out, bool full, bool feet)
 {
     SampleParams S{};
+    S.feet = feet ? 1 : 0;
     fill_common(h, S.P);
     const nufi_b200_config3d &c = h->c;
     S.P.metrics = full ? 1 : 0;

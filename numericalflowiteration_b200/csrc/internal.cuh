@@ -259,7 +259,8 @@ int ev_drain(Handle *h);                                          // blocking: f
 int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool metrics, bool defer_finish = false);
 int launch_finish(Handle *h);
 // sampling at arbitrary points (device pointers): f / ftilda at phase-space points, phi or a first derivative at positions
-int launch_sample_f(Handle *h, size_t n, size_t npts, const double *d_pts, double *d_out, bool full);
+// feet: write the foot (x.., v..) of every characteristic ([npts][2 dim]) instead of f0 at the foot
+int launch_sample_f(Handle *h, size_t n, size_t npts, const double *d_pts, double *d_out, bool full, bool feet = false);
 int launch_sample_field(Handle *h, const double *d_ref_level, int der, size_t npts, const double *d_pts, double *d_out); // runs the pending slot reduction into d_rho_partial / d_rho_full
 // tail.cu
 int tail_init(Handle *h);

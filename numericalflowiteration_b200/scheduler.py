@@ -165,6 +165,14 @@ class CudaScheduler:
         self._ck(self._L.nufi_b200_eval_f(self._h, n, len(pts), _ptr(pts), _ptr(out), int(full)))
         return out
 
+    def eval_phase_flow(self, n: int, points: np.ndarray) -> np.ndarray:
+        """Feet (x.., v..) at t = 0 of the characteristics through phase-space points [npts, 2*dim] at t_n
+        (``eval_phase_flow``, nufi/rho.hpp:98-131; like the reference, nothing is traced for n <= 1)."""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 2 * self.dim)
+        out = np.empty_like(pts)
+        self._ck(self._L.nufi_b200_eval_phase_flow(self._h, n, len(pts), _ptr(pts), _ptr(out)))
+        return out
+
     def eval_field(self, n: int, points: np.ndarray, derivative_axis: int = -1) -> np.ndarray:
         """phi_n (derivative_axis=-1) or its first derivative along an axis at positions [npts, dim]."""
         pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, self.dim)

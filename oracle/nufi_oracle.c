@@ -258,6 +258,29 @@ double orc_f_1d(int order, size_t n, double x, double u, const double *coeffs, c
     return orc_f0_1d(f, x, u);
 }
 
+/* rho.hpp:98-131: the flow map itself (dim1 only in the reference): foot (x, u) of the characteristic through (x, u) at t_n.
+ * Reference quirks kept: nothing is traced for n <= 1; the final x is wrapped with Lx*floor(x*Lx_inv) WITHOUT subtracting x_min. */
+void orc_phase_flow_1d(int order, size_t n, double *px, double *pu, const double *coeffs, const orc_conf1d *cf)
+{
+    double x = *px, u = *pu;
+    if (n > 1) {
+        const size_t stride_t = stride1(order, cf);
+        double Ex = -orc_field_1d(order, 1, x, coeffs + n * stride_t, cf);
+        u += 0.5 * cf->dt * Ex;
+        while (--n) {
+            x -= cf->dt * u;
+            Ex = -orc_field_1d(order, 1, x, coeffs + n * stride_t, cf);
+            u += cf->dt * Ex;
+        }
+        x -= cf->dt * u;
+        Ex = -orc_field_1d(order, 1, x, coeffs, cf);
+        u += 0.5 * cf->dt * Ex;
+    }
+    x = x - cf->Lx * floor(x * cf->Lx_inv);
+    *px = x;
+    *pu = u;
+}
+
 /* rho.hpp:191-232 */
 double orc_ftilda_2d(int order, size_t n, double x, double y, double u, double v, const double *coeffs,
                      const orc_conf2d *cf, const orc_f0 *f)

@@ -94,6 +94,7 @@ double orc_f0_2d(const orc_f0 *f, double x, double y, double u, double v);
 double orc_f0_3d(const orc_f0 *f, double x, double y, double z, double u, double v, double w);
 
 double orc_ftilda_1d(int order, size_t n, double x, double u, const double *coeffs, const orc_conf1d *cf, const orc_f0 *f);
+void orc_phase_flow_1d(int order, size_t n, double *x, double *u, const double *coeffs, const orc_conf1d *cf); /* rho.hpp:98-131 */
 double orc_ftilda_2d(int order, size_t n, double x, double y, double u, double v, const double *coeffs, const orc_conf2d *cf, const orc_f0 *f);
 double orc_ftilda_3d(int order, size_t n, double x, double y, double z, double u, double v, double w,
                      const double *coeffs, const orc_conf3d *cf, const orc_f0 *f);

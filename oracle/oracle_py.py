@@ -111,6 +111,19 @@ class Oracle:
         return getattr(self.lib, f"orc_{nm}_{conf.dim}d")(order, n, *[float(a) for a in xv],
                                                            np.ascontiguousarray(coeffs), C.addressof(conf), C.addressof(o))
 
+    def phase_flow(self, conf, n, coeffs, xu, order=4):
+        """Foot (x, u) of the characteristic through each row of ``xu`` at t_n (dim1, rho.hpp:98-131)."""
+        out = np.array(xu, dtype=np.float64).reshape(-1, 2).copy()
+        fn = self.lib.orc_phase_flow_1d
+        fn.argtypes = [_i, _sz, C.POINTER(C.c_double), C.POINTER(C.c_double), _dp, _p]
+        fn.restype = None
+        cc = np.ascontiguousarray(coeffs)
+        for row in out:
+            x, u = C.c_double(row[0]), C.c_double(row[1])
+            fn(order, n, C.byref(x), C.byref(u), cc, C.addressof(conf))
+            row[0], row[1] = x.value, u.value
+        return out
+
     def rho(self, conf, f0, n, coeffs, l_begin=0, l_end=None, order=4):
         """CPU-convention rho (with the leading 1) for nodes [l_begin,l_end) -- the drivers' OpenMP sweep."""
         N = _nodes(conf)
@@ -228,6 +241,19 @@ class Reference:
         nm = "f" if full else "ftilda"
         return getattr(self.lib, f"ref_{nm}_{conf.dim}d")(n, *[float(a) for a in xv], np.ascontiguousarray(coeffs),
                                                            C.addressof(conf))
+
+    def phase_flow(self, conf, n, coeffs, xu):
+        """nufi::dim1::eval_phase_flow<double,4> of the real reference on each row (x, u)."""
+        out = np.array(xu, dtype=np.float64).reshape(-1, 2).copy()
+        fn = self.lib.ref_phase_flow_1d
+        fn.argtypes = [_sz, C.POINTER(C.c_double), C.POINTER(C.c_double), _dp, _p]
+        fn.restype = None
+        cc = np.ascontiguousarray(coeffs)
+        for row in out:
+            x, u = C.c_double(row[0]), C.c_double(row[1])
+            fn(n, C.byref(x), C.byref(u), cc, C.addressof(conf))
+            row[0], row[1] = x.value, u.value
+        return out
 
     def rho(self, conf, f0, n, coeffs, l_begin=0, l_end=None):
         if f0 is not None:

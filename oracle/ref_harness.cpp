@@ -159,6 +159,11 @@ double ref_f_1d(size_t n, double x, double u, const double *coeffs, const orc_co
     c1 c = to_ref<c1>(cf);
     return nufi::dim1::eval_f<double, 4>(n, x, u, coeffs, c);
 }
+void ref_phase_flow_1d(size_t n, double *x, double *u, const double *coeffs, const orc_conf1d *cf)
+{
+    c1 c = to_ref<c1>(cf);
+    nufi::dim1::eval_phase_flow<double, 4>(n, *x, *u, coeffs, c);
+}
 double ref_f_2d(size_t n, double x, double y, double u, double v, const double *coeffs, const orc_conf2d *cf)
 {
     c2 c = to_ref<c2>(cf);

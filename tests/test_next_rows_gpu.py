@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from cases import CASES, rel_linf
-from numericalflowiteration_b200 import CudaScheduler, history_io, stride_t
+from numericalflowiteration_b200 import CudaScheduler, RangeError, history_io, stride_t
 
 pytestmark = pytest.mark.gpu
 
@@ -81,3 +81,25 @@ def test_sampling_matches_reference_point_functions(name, xpp, oracle, monkeypat
         der = tuple(int(axis == j) for j in range(d))
         want = np.array([oracle.field(conf, level, p[:d], der) for p in pts])
         assert rel_linf(g, want) <= 1e-12
+
+
+def test_eval_phase_flow_matches_reference():
+    """nufi_b200_eval_phase_flow against the committed outputs of the reference's eval_phase_flow (nufi/rho.hpp:98-131;
+    tests/golden/phase_flow_1d.npz), including its n <= 1 behaviour (nothing traced, x only reduced into the box)."""
+    import os
+
+    from cases import load_golden
+
+    conf, f0, g = load_golden("1d-two-stream")
+    pf = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "phase_flow_1d.npz"))
+    with CudaScheduler(conf, f0, device=0) as s:
+        s.upload_history(g["coeffs"], conf.Nt)
+        for n, want in zip(pf["steps"], pf["feet"]):
+            got = s.eval_phase_flow(int(n), pf["pts"])
+            dx = np.abs(got[:, 0] - want[:, 0])
+            dx = np.minimum(dx, conf.Lx - dx)  # a foot within rounding of the box edge may come back on the other side
+            assert np.max(dx) <= 1e-10 * conf.Lx, (int(n), float(np.max(dx)))
+            assert np.max(np.abs(got[:, 1] - want[:, 1])) <= 1e-10 * np.max(np.abs(want[:, 1])), int(n)
+            assert np.all(got[:, 0] >= 0) and np.all(got[:, 0] <= conf.Lx)
+        with pytest.raises(RangeError):
+            s.eval_phase_flow(conf.Nt + 1, pf["pts"])

@@ -153,3 +153,15 @@ def test_oracle_vs_live_reference(name, oracle, reference):
     phi, _ = oracle.poisson(conf, oracle.rho(conf, f0, 3, cr))
     assert rel_linf(oracle.interpolate(conf, phi), reference.interpolate(conf, phi)) <= 1e-12
     assert st == cr.size // conf.Nt
+
+
+def test_phase_flow_bit_exact(oracle):
+    """orc_phase_flow_1d == the reference's eval_phase_flow (nufi/rho.hpp:98-131) on the committed fixture, n <= 1 quirk included."""
+    import os
+
+    conf, f0, g = load_golden("1d-two-stream")
+    pf = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "phase_flow_1d.npz"))
+    for n, want in zip(pf["steps"], pf["feet"]):
+        got = oracle.phase_flow(conf, int(n), g["coeffs"], pf["pts"])
+        assert np.array_equal(got, want), int(n)
+    assert np.array_equal(pf["feet"][0][:, 1], pf["pts"][:, 1]) and np.array_equal(pf["feet"][1][:, 1], pf["pts"][:, 1])  # n <= 1: u untouched
