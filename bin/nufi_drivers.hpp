@@ -12,9 +12,14 @@
 //   --stats K   metrics every K steps (0: never)         --gpus N      use at most N devices (0: all visible)
 //   --landau    weak Landau damping f0 (1d: alpha 0.01 k 0.5; 2d: 0.05, 0.5; 3d: 0.001, 0.2 on a 10 pi box, |v| <= 6)
 //   --quiet     no per-step line                          --energy FILE write "t energy" per step
+//   --metrics-grid NX NU   (gpu 1d) integrate the statistics on an NX x NU grid of their own: the reference's two-config
+//               scheduler, bin/test_nufi_gpu_1d.cpp:216-230
+// The 1d CPU driver also writes the reference's stats.txt (t, max|E|, ||E||^2 on 256 plot points, every second step) and
+// E_<t>.txt (every 160th step) into the working directory, bin/test_nufi_cpu_1d.cpp:82-119.
 #ifndef NUFI_B200_BIN_DRIVERS_HPP
 #define NUFI_B200_BIN_DRIVERS_HPP
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -36,7 +41,7 @@ namespace nufi_drivers
 
 struct options
 {
-    size_t steps = 0, stats_every = 1, gpus = 0;
+    size_t steps = 0, stats_every = 1, gpus = 0, metrics_nx = 0, metrics_nu = 0;
     bool fused = false, landau = false, quiet = false;
     std::string energy_file;
 };
@@ -54,6 +59,7 @@ inline options parse(int argc, char **argv)
         else if (a == "--stats") o.stats_every = std::strtoull(next(), nullptr, 10);
         else if (a == "--gpus") o.gpus = std::strtoull(next(), nullptr, 10);
         else if (a == "--energy") o.energy_file = next();
+        else if (a == "--metrics-grid") { o.metrics_nx = std::strtoull(next(), nullptr, 10); o.metrics_nu = std::strtoull(next(), nullptr, 10); }
         else if (a == "--fused") o.fused = true;
         else if (a == "--landau") o.landau = true;
         else if (a == "--quiet") o.quiet = true;
@@ -105,6 +111,15 @@ template <int DIM> typename api<DIM>::conf_t make_conf(const options &o)
     return conf;
 }
 
+template <int DIM> typename api<DIM>::sched_t make_scheduler(const typename api<DIM>::conf_t &conf, const typename api<DIM>::conf_t &conf_metrics, const options &o)
+{
+    if constexpr (DIM == 1) {
+        if (o.metrics_nx && o.metrics_nu) return typename api<1>::sched_t{conf, conf_metrics};
+    }
+    (void)conf_metrics;
+    return typename api<DIM>::sched_t{conf, o.gpus};
+}
+
 struct host_buffers
 {
     std::unique_ptr<double[]> coeffs;
@@ -126,8 +141,16 @@ template <int DIM> int gpu_main(int argc, char **argv)
     typename A::conf_t conf = make_conf<DIM>(opt);
     const size_t order = 4, stride_t = tr::stride_t(conf, order), n_nodes = tr::nodes(conf), Nquad = tr::quad(conf);
 
-    typename A::sched_t sched{conf, opt.gpus};
+    typename A::conf_t conf_metrics = conf; // 1d: the grid the statistics are integrated on (bin/test_nufi_gpu_1d.cpp:216-221)
+    if (opt.metrics_nx && opt.metrics_nu) {
+        if (DIM != 1) { std::cerr << "--metrics-grid: dim 1 only" << std::endl; return 2; }
+        conf_metrics.Nx = opt.metrics_nx;
+        conf_metrics.Nu = opt.metrics_nu;
+        conf_metrics.derive();
+    }
+    typename A::sched_t sched = make_scheduler<DIM>(conf, conf_metrics, opt);
     typename A::poisson_t poiss{conf};
+    const size_t metrics_quad = tr::quad(conf_metrics);
     // one process drives all visible devices (no MPI here): this rank owns the whole quadrature range
     const size_t my_begin = 0, my_end = Nquad;
     std::cout << "Running NuFI on " << sched.device_count() << " GPU(s), " << Nquad << " quadrature points, "
@@ -136,6 +159,7 @@ template <int DIM> int gpu_main(int argc, char **argv)
     std::ofstream statistics_file("statistics.csv");
     statistics_file << R"("Time"; "L1-Norm"; "L2-Norm"; "Electric Energy"; "Kinetic Energy"; "Total Energy"; "Entropy")" << std::endl;
     statistics_file << std::scientific;
+    if (DIM == 1) statistics_file << std::setprecision(16); // bin/test_nufi_gpu_1d.cpp:282; the 2d/3d drivers keep the default 6
     std::cout << std::scientific;
     std::ofstream energy_file;
     if (!opt.energy_file.empty()) { energy_file.open(opt.energy_file); energy_file << std::setprecision(17); }
@@ -165,7 +189,7 @@ template <int DIM> int gpu_main(int argc, char **argv)
 
         if (opt.stats_every && n % opt.stats_every == 0) {
             double metrics[4]{0, 0, 0, 0};
-            sched.compute_metrics(n, my_begin, my_end);
+            sched.compute_metrics(n, 0, metrics_quad);
             sched.download_metrics(metrics);
             metrics[1] = std::sqrt(metrics[1]); // square root for the L2 norm
             const double kinetic_energy = metrics[2], total_energy = kinetic_energy + electric_energy;
@@ -175,6 +199,29 @@ template <int DIM> int gpu_main(int argc, char **argv)
     }
     std::cout << "Total compute time: " << compute_time_total << std::endl;
     return 0;
+}
+
+// stats.txt / E_<t>.txt of the reference's 1d CPU driver (bin/test_nufi_cpu_1d.cpp:82-119): every second step the field
+// E = -phi' is sampled on 256 equispaced points; one row "t  max|E|  sum E^2 * conf.dx" (widths 20, 8 digits, scientific)
+// goes to stats.txt, and every 160th step the samples go to E_<t>.txt as "x E" lines.
+inline void write_stats_1d(size_t n, const double *level, const nufi::dim1::config_t<double> &conf, std::ofstream &stats_file)
+{
+    if (n % 2 != 0) return;
+    const size_t plot_x = 256;
+    const double dx_plot = conf.Lx / plot_x, t = n * conf.dt;
+    std::ofstream file_E;
+    if (n % (10 * 16) == 0) file_E.open("E_" + std::to_string(t) + ".txt");
+    double Emax = 0, E_l2 = 0;
+    for (size_t i = 0; i < plot_x; ++i) {
+        const double x = conf.x_min + i * dx_plot;
+        const double E = -nufi::dim1::eval<double, 4, 1>(x, level, conf);
+        Emax = std::max(Emax, std::abs(E));
+        E_l2 += E * E;
+        if (file_E.is_open()) file_E << x << " " << E << std::endl;
+    }
+    E_l2 *= conf.dx; // sic: the reference scales by the grid's dx, not by dx_plot
+    stats_file << std::setw(20) << t << std::setw(20) << std::setprecision(8) << std::scientific << Emax << std::setw(20)
+               << std::setprecision(8) << std::scientific << E_l2 << std::endl;
 }
 
 // ------------------------------------------------------------------------------------------------ CPU-driver loop
@@ -192,8 +239,12 @@ template <int DIM> int cpu_main(int argc, char **argv)
     std::ofstream energy_file;
     if (!opt.energy_file.empty()) { energy_file.open(opt.energy_file); energy_file << std::setprecision(17); }
 
+    std::ofstream stats_file;
+    if (DIM == 1) stats_file.open("stats.txt");
     double total_time = 0;
-    for (size_t n = 0; n < conf.Nt; ++n) {
+    // the reference's 1d driver runs n = 0..Nt inclusive (bin/test_nufi_cpu_1d.cpp:60), its 2d/3d drivers n < Nt (_2d.cpp:63)
+    const size_t n_end = DIM == 1 ? conf.Nt + 1 : conf.Nt;
+    for (size_t n = 0; n < n_end; ++n) {
         nufi::stopwatch<double> timer;
 
         // Compute rho: the reference's loop, verbatim in shape; the first call of a step runs the sweep on the device.
@@ -206,6 +257,7 @@ template <int DIM> int cpu_main(int argc, char **argv)
         const double timer_elapsed = timer.elapsed();
         total_time += timer_elapsed;
         if (energy_file.is_open()) energy_file << n * conf.dt << " " << E_energy << "\n";
+        if constexpr (DIM == 1) write_stats_1d(n, coeffs + n * stride_t, conf, stats_file);
         if (!opt.quiet)
             std::cout << "n = " << n << " t = " << n * conf.dt << " Comp-time: " << timer_elapsed << ". Total time s.f.: " << total_time << std::endl;
     }

@@ -7,7 +7,8 @@
 // the reference: step(n) -- backtrace + NCCL all-reduce + Poisson + interpolation entirely on the devices, no host
 // round trip (what bin/test_nufi_gpu_3d.cpp:154-162 does through the host) -- plus electric_energy(), download_phi().
 //
-// Only real = double, order = 4 is implemented on the device (every reference driver instantiates <double,4>).
+// real = double; order = 3..8 as the reference instantiates (order 4, what every reference driver runs, is the specialised
+// fast path; the others run the generic Cox-de Boor kernel).
 #ifndef NUFI_B200_NUFI_CUDA_SCHEDULER_HPP
 #define NUFI_B200_NUFI_CUDA_SCHEDULER_HPP
 
@@ -60,7 +61,7 @@ template <typename Conf, size_t order> class kernel_impl
 {
     using tr = conf_traits<Conf>;
     static_assert(sizeof(Conf) == sizeof(typename tr::pod), "config_t<double> must be layout-identical to the C ABI struct");
-    static_assert(order == 4, "libnufi_b200 implements cubic B-splines (order 4) only; every reference driver uses <double,4>");
+    static_assert(order >= 3 && order <= 8, "libnufi_b200 implements the spline orders the reference instantiates: 3..8");
 
 public:
     kernel_impl(const Conf &conf, int dev) : conf_{conf}
@@ -83,6 +84,12 @@ public:
     void upload_phi(size_t n, const double *coeffs) { ck(nufi_b200_upload_phi(h_, n, coeffs)); }
     void compute_metrics(size_t n, size_t q_min, size_t q_max) { ck(nufi_b200_compute_metrics(h_, n, q_min, q_max)); }
     void download_metrics(double *metrics) { ck(nufi_b200_download_metrics(h_, metrics)); }
+    // dim 1: metrics on a grid of their own (the reference's cuda_kernel(conf, conf_metrics, dev), nufi/cuda_kernel.cu:97-110)
+    void set_metrics_grid(const Conf &conf_metrics)
+    {
+        static_assert(tr::dim == 1, "a separate metrics grid exists for dim1 only");
+        ck(nufi_b200_set_metrics_grid_1d(h_, reinterpret_cast<const nufi_b200_config1d *>(&conf_metrics)));
+    }
 
     // beyond the reference
     void step(size_t n) { ck(nufi_b200_step(h_, n)); }
@@ -176,6 +183,7 @@ public:
     void sync() { for (auto &k : kernels) k.sync(); }
     size_t device_count() const noexcept { return kernels.size(); }
     kernel_impl<Conf, order> &kernel(size_t i) { return kernels[i]; }
+    void set_metrics_grid(const Conf &conf_metrics) { for (auto &k : kernels) k.set_metrics_grid(conf_metrics); }
 
 private:
     template <typename F> void split(size_t q_begin, size_t q_end, F &&f)
@@ -215,20 +223,38 @@ template <typename real> struct require_double
     {                                                                                                                   \
     public:                                                                                                             \
         explicit cuda_scheduler(const config_t<real> &conf, size_t max_devices = 0) : detail::scheduler_impl<config_t<real>, order>(conf, max_devices) {} \
-        /* dim1 in the reference has a second constructor with a separate metrics grid (cuda_scheduler.hpp:65-85); */   \
-        /* the device library integrates the metrics on the grid of `conf`, so the two must agree. */                   \
-        cuda_scheduler(const config_t<real> &conf, const config_t<real> &conf_metrics) : detail::scheduler_impl<config_t<real>, order>(conf, 0) \
-        {                                                                                                               \
-            if (std::memcmp(&conf, &conf_metrics, sizeof(conf)) != 0)                                                   \
-                throw std::invalid_argument("cuda_scheduler: a separate metrics grid is not supported by libnufi_b200"); \
-        }                                                                                                               \
     };                                                                                                                  \
     }
 
-NUFI_B200_DEFINE_SCHEDULER(dim1)
 NUFI_B200_DEFINE_SCHEDULER(dim2)
 NUFI_B200_DEFINE_SCHEDULER(dim3)
 #undef NUFI_B200_DEFINE_SCHEDULER
+
+// dim1 has a second constructor with a separate metrics grid (nufi/cuda_kernel.hpp:36-37, nufi/cuda_scheduler.hpp:65-85):
+// compute_metrics then integrates over the (x,u) nodes of conf_metrics while eval_f uses the field grid of conf
+// (nufi/cuda_kernel.cu:55-70).
+namespace dim1
+{
+template <typename real, size_t order> class cuda_kernel : detail::require_double<real>, public detail::kernel_impl<config_t<real>, order>
+{
+public:
+    cuda_kernel(const config_t<real> &conf, int dev = -1) : detail::kernel_impl<config_t<real>, order>(conf, dev) {}
+    cuda_kernel(const config_t<real> &conf, const config_t<real> &conf_metrics, int dev = -1) : detail::kernel_impl<config_t<real>, order>(conf, dev)
+    {
+        this->set_metrics_grid(conf_metrics);
+    }
+};
+template <typename real, size_t order> class cuda_scheduler : detail::require_double<real>, public detail::scheduler_impl<config_t<real>, order>
+{
+public:
+    explicit cuda_scheduler(const config_t<real> &conf, size_t max_devices = 0) : detail::scheduler_impl<config_t<real>, order>(conf, max_devices) {}
+    cuda_scheduler(const config_t<real> &conf, const config_t<real> &conf_metrics) : detail::scheduler_impl<config_t<real>, order>(conf, 0)
+    {
+        this->set_metrics_grid(conf_metrics);
+    }
+};
+} // namespace dim1
+
 
 } // namespace nufi
 

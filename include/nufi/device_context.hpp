@@ -1,12 +1,25 @@
-// nufi/device_context.hpp -- a cached device handle per configuration, for the reference's FREE functions and
-// handle-less classes (eval_rho, interpolate, poisson<real>), which take only (coeffs, conf).  Not in the reference:
-// there these run on the host and need no state.
+// nufi/device_context.hpp -- cached device handles for the reference's FREE functions and handle-less classes
+// (eval_rho, interpolate, poisson<real>), which take only (coeffs, conf).  Not in the reference: there these run on the
+// host and need no state.
+//
+// A `mirror` pairs one device handle with the host coefficient history it shadows.  Every level is identified by a hash of
+// ALL of its bytes; a level is re-uploaded exactly when its hash changed, so an in-place edit of any coefficient of any
+// level is seen the next time the history is validated.  Validation (hashing levels [0, n)) happens
+//   * whenever rho of a step is computed, and
+//   * whenever a node is asked for a second time from the cached rho of a step (a driver's sweep asks for every node once,
+//     bin/test_nufi_cpu_2d.cpp:68-72; a repeated question means a new sweep, possibly after an edit of the history);
+// in between -- inside one sweep -- a query is a table lookup.  nufi::invalidate_device_cache() forces re-validation.
+// Mirrors are looked up by (configuration bytes, f0_sel) in a small table and handed out as shared_ptr, so a call holds its
+// mirror alive while another thread asks for a different configuration.
 #ifndef NUFI_B200_NUFI_DEVICE_CONTEXT_HPP
 #define NUFI_B200_NUFI_DEVICE_CONTEXT_HPP
 
+#include <atomic>
 #include <cstring>
+#include <list>
 #include <memory>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "cuda_scheduler.hpp"
@@ -17,8 +30,35 @@ namespace nufi
 namespace detail
 {
 
-// Device-side mirror of a host coefficient history: remembers a sampled fingerprint of every level it uploaded and
-// re-uploads a level only when the host copy changed (in the time loop: exactly the one new level per step).
+inline std::atomic<unsigned long long> &cache_generation()
+{
+    static std::atomic<unsigned long long> g{1};
+    return g;
+}
+
+// 64-bit hash of a whole level (every byte takes part): multiply-xorshift rounds over 8-byte words, four lanes
+inline unsigned long long hash_level(const double *level, size_t count)
+{
+    unsigned long long h[4] = {0x9e3779b97f4a7c15ull, 0xbf58476d1ce4e5b9ull, 0x94d049bb133111ebull, 0xd6e8feb86659fd93ull};
+    size_t i = 0;
+    for (; i + 4 <= count; i += 4)
+        for (int k = 0; k < 4; ++k) {
+            unsigned long long w;
+            std::memcpy(&w, level + i + k, 8);
+            h[k] = (h[k] ^ w) * 0x9fb21c651e98df25ull;
+            h[k] ^= h[k] >> 29;
+        }
+    for (; i < count; ++i) {
+        unsigned long long w;
+        std::memcpy(&w, level + i, 8);
+        h[0] = (h[0] ^ w) * 0x9fb21c651e98df25ull;
+        h[0] ^= h[0] >> 29;
+    }
+    unsigned long long r = h[0];
+    for (int k = 1; k < 4; ++k) r = (r ^ h[k]) * 0xff51afd7ed558ccdull, r ^= r >> 32;
+    return r | 1ull; // never 0 (= "not uploaded")
+}
+
 template <typename Conf, size_t order> class mirror
 {
     using tr = conf_traits<Conf>;
@@ -26,32 +66,19 @@ template <typename Conf, size_t order> class mirror
 public:
     explicit mirror(const Conf &c) : conf{c}, kern{c, -1}, stride{tr::stride_t(c, order)}, prints(c.Nt + 1, 0) {}
 
-    bool same_config(const Conf &c) const { return std::memcmp(&c, &conf, sizeof(Conf)) == 0; }
-
-    // make device levels [0, n) equal to coeffs[0 .. n*stride_t)
-    void sync_levels(size_t n, const double *coeffs)
-    {
-        for (size_t m = 0; m < n && m < prints.size(); ++m) {
-            const unsigned long long fp = fingerprint(coeffs + m * stride);
-            if (fp != prints[m]) {
-                kern.upload_phi(m, coeffs);
-                prints[m] = fp;
-            }
-        }
-    }
-
-    // rho of step n for all nodes (CPU convention, with the leading 1); cached per (n, history fingerprint)
-    const std::vector<double> &rho(size_t n, const double *coeffs)
+    // rho of step n at node l (CPU convention, with the leading 1)
+    double rho_at(size_t n, size_t l, const double *coeffs)
     {
         std::lock_guard<std::mutex> lock(mtx);
-        const unsigned long long key = n == 0 ? 1 : fingerprint(coeffs + (n - 1) * stride) ^ (0x9e3779b97f4a7c15ull * (n + 1));
-        if (!(have && cached_n == n && cached_key == key && cached_ptr == coeffs)) {
-            sync_levels(n, coeffs);
-            cache.resize(tr::nodes(conf));
-            kern.eval_rho_all(n, cache.data());
-            have = true; cached_n = n; cached_key = key; cached_ptr = coeffs;
-        }
-        return cache;
+        refresh(n, coeffs, l);
+        return cache[l];
+    }
+    // rho of step n at all nodes
+    void rho_all(size_t n, const double *coeffs, double *out)
+    {
+        std::lock_guard<std::mutex> lock(mtx);
+        refresh(n, coeffs, tr::nodes(conf)); // "every node": always re-validates
+        std::memcpy(out, cache.data(), sizeof(double) * cache.size());
     }
 
     // feet (x.., v..) at t = 0 of the characteristics through `npts` phase-space points at t_n (needs levels 0..n of coeffs)
@@ -62,19 +89,46 @@ public:
         kern.eval_phase_flow(n, npts, points, feet);
     }
 
-    kernel_impl<Conf, order> &kernel() { return kern; }
+    // nodal values -> one level of coefficients (host buffers); does not touch the mirrored history
+    void interpolate(const double *values, double *coeffs_level)
+    {
+        std::lock_guard<std::mutex> lock(mtx);
+        cuda::check(nufi_b200_interpolate(kern.handle(), values, coeffs_level), nufi_b200_last_error(kern.handle()));
+    }
 
 private:
-    unsigned long long fingerprint(const double *level) const
+    // make device levels [0, n) equal to coeffs[0 .. n*stride_t); returns a hash of the whole range
+    unsigned long long sync_levels(size_t n, const double *coeffs)
     {
-        unsigned long long h = 0xcbf29ce484222325ull;
-        const size_t step = stride > 64 ? stride / 61 : 1;
-        for (size_t i = 0; i < stride; i += step) {
-            unsigned long long b;
-            std::memcpy(&b, level + i, 8);
-            h = (h ^ b) * 0x100000001b3ull;
+        unsigned long long all = 0x2545f4914f6cdd1dull;
+        for (size_t m = 0; m < n && m < prints.size(); ++m) {
+            const unsigned long long fp = hash_level(coeffs + m * stride, stride);
+            if (fp != prints[m]) {
+                kern.upload_phi(m, coeffs);
+                prints[m] = fp;
+            }
+            all = (all ^ fp) * 0x100000001b3ull;
         }
-        return h | 1ull; // never 0 (= "not uploaded")
+        return all;
+    }
+
+    // l == nodes: the caller wants every node
+    void refresh(size_t n, const double *coeffs, size_t l)
+    {
+        const size_t nodes = tr::nodes(conf);
+        const unsigned long long gen = cache_generation().load();
+        const bool same_sweep = have && cached_n == n && cached_ptr == coeffs && cached_gen == gen && l < nodes && !served[l];
+        if (!same_sweep) {
+            const unsigned long long key = sync_levels(n, coeffs); // hashes every byte of levels [0, n)
+            if (!(have && cached_n == n && cached_key == key)) {
+                cache.resize(nodes);
+                kern.eval_rho_all(n, cache.data());
+                have = true; cached_n = n; cached_key = key;
+            }
+            cached_ptr = coeffs; cached_gen = gen;
+            served.assign(nodes, 0);
+        }
+        if (l < nodes) served[l] = 1;
     }
 
     Conf conf;
@@ -83,23 +137,36 @@ private:
     std::vector<unsigned long long> prints;
     std::mutex mtx;
     std::vector<double> cache;
+    std::vector<unsigned char> served; // nodes already answered from `cache` since it was last validated
     bool have = false;
     size_t cached_n = 0;
-    unsigned long long cached_key = 0;
+    unsigned long long cached_key = 0, cached_gen = 0;
     const double *cached_ptr = nullptr;
 };
 
-// one mirror per configuration type; re-created when a different configuration shows up
-template <typename Conf, size_t order> mirror<Conf, order> &context(const Conf &conf)
+// mirrors by (configuration bytes, f0_sel bytes); the few most recently used are kept
+template <typename Conf, size_t order> std::shared_ptr<mirror<Conf, order>> context(const Conf &conf)
 {
+    using entry = std::pair<std::string, std::shared_ptr<mirror<Conf, order>>>;
     static std::mutex mtx;
-    static std::unique_ptr<mirror<Conf, order>> ctx;
+    static std::list<entry> table;
+    std::string key(reinterpret_cast<const char *>(&conf), sizeof(Conf));
+    key.append(reinterpret_cast<const char *>(&Conf::f0_sel), sizeof(Conf::f0_sel));
     std::lock_guard<std::mutex> lock(mtx);
-    if (!ctx || !ctx->same_config(conf)) ctx.reset(new mirror<Conf, order>(conf));
-    return *ctx;
+    for (auto it = table.begin(); it != table.end(); ++it)
+        if (it->first == key) {
+            table.splice(table.begin(), table, it); // most recently used first
+            return table.front().second;
+        }
+    table.emplace_front(key, std::make_shared<mirror<Conf, order>>(conf));
+    if (table.size() > 4) table.pop_back(); // a caller still using the dropped mirror keeps it alive through its shared_ptr
+    return table.front().second;
 }
 
 } // namespace detail
+
+// Forget what the device mirrors assume about host histories: the next eval_rho / eval_phase_flow re-hashes every level.
+inline void invalidate_device_cache() { detail::cache_generation().fetch_add(1); }
 
 } // namespace nufi
 

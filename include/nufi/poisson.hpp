@@ -20,6 +20,12 @@ namespace nufi
         poisson() = delete;                                                                                             \
         explicit poisson(const config_t<real> &param) : kern{without_history(param), -1}, param_{param} {}              \
         config_t<real> conf() const noexcept { return param_; }                                                         \
+        /* nufi/poisson.hpp:49, poisson.cpp:51-64: re-plan for a new grid */                                            \
+        void conf(const config_t<real> &new_param)                                                                      \
+        {                                                                                                               \
+            kern = detail::kernel_impl<config_t<real>, 4>{without_history(new_param), -1};                              \
+            param_ = new_param;                                                                                         \
+        }                                                                                                               \
         real solve(real *data)                                                                                          \
         {                                                                                                               \
             double e = 0;                                                                                               \

@@ -19,13 +19,12 @@ namespace nufi
     template <typename real, size_t order> real eval_rho(size_t n, size_t l, const real *coeffs, const config_t<real> &conf) \
     {                                                                                                                   \
         static_assert(std::is_same<real, double>::value, "libnufi_b200 computes in FP64");                              \
-        return detail::context<config_t<real>, order>(conf).rho(n, coeffs)[l];                                          \
+        return detail::context<config_t<real>, order>(conf)->rho_at(n, l, coeffs);                                      \
     }                                                                                                                   \
     template <typename real, size_t order> void eval_rho_all(size_t n, real *rho, const real *coeffs, const config_t<real> &conf) \
     {                                                                                                                   \
         static_assert(std::is_same<real, double>::value, "libnufi_b200 computes in FP64");                              \
-        const std::vector<double> &r = detail::context<config_t<real>, order>(conf).rho(n, coeffs);                     \
-        std::memcpy(rho, r.data(), sizeof(double) * r.size());                                                          \
+        detail::context<config_t<real>, order>(conf)->rho_all(n, coeffs, rho);                                          \
     }                                                                                                                   \
     }
 
@@ -37,7 +36,7 @@ template <typename real, size_t order> void eval_phase_flow(size_t n, real &x, r
 {
     static_assert(std::is_same<real, double>::value, "libnufi_b200 computes in FP64");
     double in[2] = {x, u}, out[2];
-    detail::context<config_t<real>, order>(conf).phase_flow(n, 1, in, out, coeffs);
+    detail::context<config_t<real>, order>(conf)->phase_flow(n, 1, in, out, coeffs);
     x = out[0];
     u = out[1];
 }
@@ -45,7 +44,7 @@ template <typename real, size_t order>
 void eval_phase_flow_all(size_t n, size_t npts, const real *points /*[npts][2]: x, u*/, real *feet, const real *coeffs, const config_t<real> &conf)
 {
     static_assert(std::is_same<real, double>::value, "libnufi_b200 computes in FP64");
-    detail::context<config_t<real>, order>(conf).phase_flow(n, npts, points, feet, coeffs);
+    detail::context<config_t<real>, order>(conf)->phase_flow(n, npts, points, feet, coeffs);
 }
 } // namespace dim1
 

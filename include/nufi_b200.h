@@ -97,7 +97,11 @@ typedef struct {
 
 /* ---- lifetime (cuda_scheduler ctor, nufi/cuda_scheduler.hpp:43-63; cuda_kernel ctor nufi/cuda_kernel.cu:81-110,
  *      273-287, 468-483).  Allocates the (Nt+1)-level device history, rho, metrics on `device`
- *      (-1 = current device).  order must be 4 (cubic; every reference driver instantiates <double,4>). ---- */
+ *      (-1 = current device).  order = 3..8, the orders the reference instantiates (nufi/cuda_kernel.cu:191-203, 373-385,
+ *      575-587).  order 4 (cubic; what every reference driver runs) takes the specialised kernels (per-cell polynomial level
+ *      formats, shared-memory staging); the other orders run the generic Cox-de Boor kernel on the reference layout (global
+ *      memory variant, one point per thread).  stride_t = prod_d (N_d + order - 1) everywhere below.
+ *      f0 must have the period of the box: k*L_d = 2*pi*m for every dimension d, else ERR_ARG. ---- */
 int nufi_b200_create_1d(const nufi_b200_config1d *conf, int order, const nufi_b200_f0 *f0, int device, nufi_b200_handle **out);
 int nufi_b200_create_2d(const nufi_b200_config2d *conf, int order, const nufi_b200_f0 *f0, int device, nufi_b200_handle **out);
 int nufi_b200_create_3d(const nufi_b200_config3d *conf, int order, const nufi_b200_f0 *f0, int device, nufi_b200_handle **out);
@@ -118,6 +122,12 @@ int nufi_b200_upload_phi(nufi_b200_handle *h, size_t n, const double *coeffs_bas
  * metrics[0..3] += {int f, int f^2, kinetic energy, entropy}.  Weights as the reference writes them. */
 int nufi_b200_compute_metrics(nufi_b200_handle *h, size_t n, size_t q_begin, size_t q_end);
 int nufi_b200_download_metrics(nufi_b200_handle *h, double *metrics4_host);
+/* dim 1 only: the reference's second constructor cuda_scheduler(conf, conf_metrics) / cuda_kernel(conf, conf_metrics, dev)
+ * (nufi/cuda_scheduler.hpp:65-85, nufi/cuda_kernel.cu:97-110) integrates the metrics over the (x,u) grid of conf_metrics --
+ * nodes x_min + ix*dx, u_min + iu*du + du/2, weight du*dx, flat index q = ix*Nu + iu, all taken from conf_metrics -- while
+ * eval_f uses the field grid of conf (nufi/cuda_kernel.cu:55-70).  After this call compute_metrics does that;
+ * conf_metrics == NULL restores the handle's own grid. */
+int nufi_b200_set_metrics_grid_1d(nufi_b200_handle *h, const nufi_b200_config1d *conf_metrics);
 
 /* ---- CPU-driver-shaped entry points (bin/test_nufi_cpu_{1,2,3}d.cpp loop body) ---- */
 /* the whole "#pragma omp parallel for: rho[l] = eval_rho(n,l,coeffs,conf)" sweep in one call; blocking;

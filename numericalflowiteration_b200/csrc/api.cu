@@ -3,6 +3,7 @@
 // Mirrors the surface of nufi::dim{1,2,3}::cuda_kernel (nufi/cuda_kernel.cu:81-189, 273-371, 468-573).
 #include "internal.cuh"
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -82,13 +83,27 @@ int create_common(const nufi_b200_config3d &c, int dim, int order, const nufi_b2
 {
     if (!out) return fail(nullptr, NUFI_B200_ERR_ARG, "out is NULL");
     *out = nullptr;
-    if (order != 4)
-        return fail(nullptr, NUFI_B200_ERR_ARG, "only order 4 (cubic B-splines) is implemented; every reference driver uses <double,4>");
-    if (c.Nx < 4 || (dim >= 2 && c.Ny < 4) || (dim >= 3 && c.Nz < 4) || c.Nu == 0 || (dim >= 2 && c.Nv == 0) || (dim >= 3 && c.Nw == 0))
-        return fail(nullptr, NUFI_B200_ERR_ARG, "grid too small: need N >= 4 nodes per spatial dimension and >= 1 velocity node");
+    if (order < 3 || order > 8) // the orders the reference instantiates (nufi/cuda_kernel.cu:191-203, 373-385, 575-587)
+        return fail(nullptr, NUFI_B200_ERR_ARG, "spline order must be 3..8 (4 = cubic, what every reference driver uses, is the specialised fast path)");
+    const size_t o = static_cast<size_t>(order), halo = o - 1;
+    const size_t nmin = o < 4 ? 4 : o;
+    if (c.Nx < nmin || (dim >= 2 && c.Ny < nmin) || (dim >= 3 && c.Nz < nmin) || c.Nu == 0 || (dim >= 2 && c.Nv == 0) || (dim >= 3 && c.Nw == 0))
+        return fail(nullptr, NUFI_B200_ERR_ARG, "grid too small: need N >= max(4, order) nodes per spatial dimension and >= 1 velocity node");
     if (c.Nx > (1u << 20) || c.Ny > (1u << 20) || c.Nz > (1u << 20))
         return fail(nullptr, NUFI_B200_ERR_ARG, "grid too large");
     if (!f0 || f0->kind < 0 || f0->kind > (dim == 3 ? 2 : 1)) return fail(nullptr, NUFI_B200_ERR_ARG, "unknown f0 kind");
+    {   // f0 is evaluated at the periodic image of the foot inside the box (the reference evaluates it at the unwrapped position):
+        // the two agree iff f0 has the period of the box, i.e. k*L is a multiple of 2 pi in every dimension.  Refuse anything else.
+        const double k = f0->p[1];
+        const double Ls[3] = {c.Lx, c.Ly, c.Lz};
+        for (int d = 0; d < dim; ++d) {
+            const double periods = k * Ls[d] / (2.0 * 3.14159265358979323846);
+            if (!(std::fabs(periods - std::nearbyint(periods)) <= 1e-9 * (1.0 + std::fabs(periods))))
+                return fail(nullptr, NUFI_B200_ERR_ARG,
+                            "f0 is not periodic in the box: its wavenumber k = p[1] must satisfy k*L = 2*pi*m in every dimension "
+                            "(the device evaluates f0 at the periodic image of the foot of the characteristic)");
+        }
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -105,9 +120,13 @@ int create_common(const nufi_b200_config3d &c, int dim, int order, const nufi_b2
     h->dim = dim; h->order = order; h->device = device; h->c = c; h->f0 = *f0; h->Nt = c.Nt;
     h->n_nodes = c.Nx * c.Ny * c.Nz;
     h->n_vel = c.Nu * c.Nv * c.Nw;
-    h->stride_t = (c.Nx + 3) * (dim >= 2 ? c.Ny + 3 : 1) * (dim >= 3 ? c.Nz + 3 : 1);
+    h->stride_t = (c.Nx + halo) * (dim >= 2 ? c.Ny + halo : 1) * (dim >= 3 ? c.Nz + halo : 1);
     // device level format
-    if (dim == 1) {
+    if (order != 4) { // generic orders: the reference layout itself (halo of order-1), padded to a 16-byte multiple
+        h->sx = static_cast<int>(c.Nx + halo);
+        h->sxy = dim >= 2 ? h->sx * static_cast<int>(c.Ny + halo) : 0;
+        h->level_stride = (h->stride_t + 1) & ~size_t(1);
+    } else if (dim == 1) {
         h->level_stride = (3 * c.Nx + 1) & ~size_t(1); // per-cell quadratics [p0 p1 p2] (tail.cu), 16-byte multiple
         h->raw_stride = (c.Nx + 3 + 1) & ~size_t(1);
         h->sx = 0; h->sxy = 0;
@@ -155,7 +174,7 @@ int create_common(const nufi_b200_config3d &c, int dim, int order, const nufi_b2
     const size_t hist_bytes = (c.Nt + 1) * h->level_stride * sizeof(double);
     CREATE_CHECK(cudaMalloc(&h->d_hist, hist_bytes));
     CREATE_CHECK(cudaMemsetAsync(h->d_hist, 0, hist_bytes, h->stream));
-    if (dim == 1 || h->xpp) {
+    if ((dim == 1 && order == 4) || h->xpp) {
         CREATE_CHECK(cudaMalloc(&h->d_raw, (c.Nt + 1) * h->raw_stride * sizeof(double)));
         CREATE_CHECK(cudaMemsetAsync(h->d_raw, 0, (c.Nt + 1) * h->raw_stride * sizeof(double), h->stream));
     }
@@ -306,7 +325,7 @@ int nufi_b200_compute_metrics(nufi_b200_handle *h, size_t n, size_t q_begin, siz
 {
     ENTER(h);
     if (n > hh->Nt) return fail(hh, NUFI_B200_ERR_RANGE, "Time-step out of range.");
-    const size_t nq = hh->n_nodes * hh->n_vel;
+    const size_t nq = hh->mgrid_set ? hh->mconf.Nx * hh->mconf.Nu : hh->n_nodes * hh->n_vel;
     if (q_begin > q_end || q_end > nq) return fail(hh, NUFI_B200_ERR_RANGE, "quadrature range out of bounds");
     if (q_begin == q_end) {
         NUFI_CUDA_CHECK(hh, cudaMemsetAsync(hh->d_metrics, 0, sizeof(double) * 4, hh->stream));
@@ -315,6 +334,21 @@ int nufi_b200_compute_metrics(nufi_b200_handle *h, size_t n, size_t q_begin, siz
     int rc = check_levels(hh, n == 0 ? 0 : n + 1, "compute_metrics");
     if (rc) return rc;
     return launch_backtrace(hh, n, q_begin, q_end, true);
+}
+
+int nufi_b200_set_metrics_grid_1d(nufi_b200_handle *h, const nufi_b200_config1d *conf_metrics)
+{
+    ENTER(h);
+    if (hh->dim != 1) return fail(hh, NUFI_B200_ERR_ARG, "a separate metrics grid exists for dim 1 only (nufi/cuda_scheduler.hpp:65-85)");
+    if (!conf_metrics) { // back to the grid of the handle's own configuration
+        hh->mgrid_set = false;
+        return NUFI_B200_OK;
+    }
+    if (conf_metrics->Nx == 0 || conf_metrics->Nu == 0 || conf_metrics->Nx >= (1ull << 31) || conf_metrics->Nu >= (1ull << 31))
+        return fail(hh, NUFI_B200_ERR_ARG, "metrics grid: Nx and Nu must be positive (and below 2^31)");
+    hh->mconf = *conf_metrics;
+    hh->mgrid_set = true;
+    return NUFI_B200_OK;
 }
 
 int nufi_b200_download_metrics(nufi_b200_handle *h, double *m)
@@ -663,6 +697,6 @@ int nufi_b200_device_count(int *count)
 
 int nufi_b200_device_of(const nufi_b200_handle *h) { return h ? H(h)->device : -1; }
 
-const char *nufi_b200_version(void) { return "nufi_b200 0.1 (sm_100a)"; }
+const char *nufi_b200_version(void) { return "nufi_b200 0.2 (sm_100a)"; }
 
 } // extern "C"

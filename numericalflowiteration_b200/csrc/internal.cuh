@@ -33,6 +33,9 @@ struct BtParams
     double ug0, vg0, wg0, dug, dvg, dwg; // metrics: GPU-form nodes u_min + i*du + du/2 (conf.du)
     int f0_kind;
     double f0p[4];
+    // 1d metrics on a grid of their own (nufi/cuda_kernel.cu:55-70): node l sits at mx_min + l*mdx and is located in the field grid
+    int mgrid;
+    double mx_min, mdx, Lx, Lx_inv, dx_inv;
     // work decomposition (see backtrace.cu)
     unsigned long long q_begin, q_end, Nvel;
     unsigned long long Nvel_loc, vstride, voff; // this launch traces velocity nodes voff, voff+vstride, ... (Nvel_loc of them)
@@ -53,6 +56,18 @@ struct BtParams
     // staged variant: shared-memory ring of `stages` stages, each a chunk of Lc consecutive levels
     int Lc, stages;
     unsigned int stage_bytes;
+};
+
+// sampling kernels (sample_f_kernel): f / ftilda / the flow map at arbitrary phase-space points
+struct SampleParams
+{
+    BtParams P;
+    double Lx, Ly, Lz, Lx_inv, Ly_inv, Lz_inv, dx_inv, dy_inv, dz_inv;
+    const double *pts; // [npts][2*dim]: x.., v..
+    double *out;
+    size_t npts;
+    int with_first_half_kick; // 1: eval_f (nufi/rho.hpp:63-96, 234-281, 369-426), 0: eval_ftilda
+    int feet;                 // 1: write the foot (x.., v..) of the characteristic instead of f0 there (eval_phase_flow, rho.hpp:98-131)
 };
 
 struct FinishParams
@@ -214,6 +229,8 @@ struct Handle
     PeerState px;
     bool fin_push = false;       // the pending slot reduction also pushes to the peers (finish_push_kernel)
     int tn_force = 0;            // nodes per tile forced by nufi_b200_set_tile_nodes (0: automatic)
+    bool mgrid_set = false;      // 1d: compute_metrics integrates over `mconf`'s (x,u) grid instead of the field grid's
+    nufi_b200_config1d mconf{};
     int variant_force = 0;
     const char *last_variant = "none";
     char variant_buf[64] = {0};
@@ -254,6 +271,11 @@ int fail(Handle *h, int code, const std::string &msg);
 constexpr size_t kEvRingPairs = 256;
 int ev_acquire(Handle *h, cudaEvent_t *start, cudaEvent_t *stop); // next pair (drains the oldest when the ring is full)
 int ev_drain(Handle *h);                                          // blocking: fold all pending pairs into the totals
+// backtrace_generic.cu: the backtrace / sampling kernels for spline orders 3, 5..8 (global-memory variant, one point per thread)
+cudaError_t launch_backtrace_generic(int order, int dim, const BtParams &P, const EpilogueParams &E, unsigned grid, unsigned threads,
+                                     size_t smem_bytes, cudaStream_t st);
+int generic_max_threads(int dim);
+cudaError_t launch_sample_f_generic(int order, int dim, const SampleParams &S, unsigned blocks, cudaStream_t st);
 // backtrace.cu
 // defer_finish: leave the slot reduction to the field tail (fused step); otherwise finish_rho_kernel is launched
 int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool metrics, bool defer_finish = false);

@@ -111,6 +111,8 @@ struct ExpandParams
     size_t level_doubles; // device level size
     double g1;            // 1d: -dt*dx_inv
     int xpp;              // 2d/3d: level = per (row, cell) cubic in the x offset, [Q01: Nx x (a0,a1)][Q23: Nx x (a2,a3)] per row
+    int halo;             // order - 1 periodic halo nodes per dimension in the reference layout (3 for the cubic formats above)
+    int pp1d;             // 1d, order 4: level = per-cell quadratics of dt*E, raw level kept beside it; else level = raw layout
 };
 
 // xpp level + raw reference-format level from a coefficient source.  PERIODIC: src holds Nx*Ny*Nz periodic coefficients;
@@ -170,11 +172,11 @@ __global__ void expand_kernel(const double *src, double *level, ExpandParams E, 
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int i = static_cast<int>(idx % E.sx);
         const size_t rest = idx / E.sx;
-        const int rows = E.Ny + 3;
+        const int rows = E.dim >= 2 ? E.Ny + E.halo : 1;
         const int j = static_cast<int>(rest % rows);
         const int k = static_cast<int>(rest / rows);
         double v = 0;
-        if (i < E.Nx + 3 && (E.dim < 3 ? k == 0 : k < E.Nz + 3))
+        if (i < E.Nx + E.halo && (E.dim < 3 ? k == 0 : k < E.Nz + E.halo))
             v = src[(static_cast<size_t>(k % E.Nz) * E.Ny + (j % E.Ny)) * E.Nx + (i % E.Nx)];
         level[idx] = v;
     }
@@ -213,7 +215,7 @@ __global__ void expand1d_kernel(const double *src, double *raw, double *pp, Expa
 // reference-format level (with halo, row stride Nx+3) -> device format
 __global__ void ref_to_device_kernel(const double *ref, double *level, double *raw1d, ExpandParams E)
 {
-    if (E.dim == 1) {
+    if (E.pp1d) {
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < E.Nx + 3; i += gridDim.x * blockDim.x) raw1d[i] = ref[i];
         for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < E.Nx; k += gridDim.x * blockDim.x) {
             double p0, p1, p2;
@@ -226,7 +228,7 @@ __global__ void ref_to_device_kernel(const double *ref, double *level, double *r
         return;
     }
     const size_t total = E.level_doubles;
-    const int rx = E.Nx + 3, ry = E.Ny + 3;
+    const int rx = E.Nx + E.halo, ry = E.dim >= 2 ? E.Ny + E.halo : 1;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int i = static_cast<int>(idx % E.sx);
@@ -234,20 +236,20 @@ __global__ void ref_to_device_kernel(const double *ref, double *level, double *r
         const int j = static_cast<int>(rest % ry);
         const int k = static_cast<int>(rest / ry);
         double v = 0;
-        if (i < rx && (E.dim < 3 ? k == 0 : k < E.Nz + 3)) v = ref[(static_cast<size_t>(k) * ry + j) * rx + i];
+        if (i < rx && (E.dim < 3 ? k == 0 : k < E.Nz + E.halo)) v = ref[(static_cast<size_t>(k) * ry + j) * rx + i];
         level[idx] = v;
     }
 }
 
 __global__ void device_to_ref_kernel(const double *level, const double *raw1d, double *ref, ExpandParams E)
 {
-    if (E.dim == 1 || E.xpp) { // the raw reference-format level is kept beside the pp-form
+    if (E.pp1d || E.xpp) { // the raw reference-format level is kept beside the pp-form
         const size_t total = static_cast<size_t>(E.Nx + 3) * (E.dim >= 2 ? E.Ny + 3 : 1) * (E.dim >= 3 ? E.Nz + 3 : 1);
         for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x)
             ref[i] = raw1d[i];
         return;
     }
-    const int rx = E.Nx + 3, ry = E.Ny + 3, rz = E.dim == 3 ? E.Nz + 3 : 1;
+    const int rx = E.Nx + E.halo, ry = E.dim >= 2 ? E.Ny + E.halo : 1, rz = E.dim == 3 ? E.Nz + E.halo : 1;
     const size_t total = static_cast<size_t>(rx) * ry * rz;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -581,7 +583,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
     TAIL_MARK(4);
     // ---- level n: periodic coefficients (real part) -> device level format
     const ExpandParams &E = S.E;
-    if (E.dim == 1) {
+    if (E.pp1d) {
         for (int i = threadIdx.x; i < Nx + 3; i += blockDim.x) S.raw1d[i] = cur[i % Nx].x;
         for (int k = threadIdx.x; k < Nx; k += blockDim.x) {
             double c[4], p0, p1, p2;
@@ -597,14 +599,14 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
         auto get = [&](size_t i) { return cur[i].x; };
         write_xpp<true>(get, S.level, S.raw1d, E, threadIdx.x, blockDim.x);
     } else {
-        const int rows = Ny + 3;
+        const int rows = E.dim >= 2 ? Ny + E.halo : 1;
         for (size_t idx = threadIdx.x; idx < E.level_doubles; idx += blockDim.x) {
             const int i = static_cast<int>(idx % E.sx);
             const size_t rest = idx / E.sx;
             const int j = static_cast<int>(rest % rows);
             const int k = static_cast<int>(rest / rows);
             double v = 0;
-            if (i < Nx + 3 && (E.dim < 3 ? k == 0 : k < Nz + 3)) v = cur[((k % Nz) * Ny + (j % Ny)) * Nx + (i % Nx)].x;
+            if (i < Nx + E.halo && (E.dim < 3 ? k == 0 : k < Nz + E.halo)) v = cur[((k % Nz) * Ny + (j % Ny)) * Nx + (i % Nx)].x;
             S.level[idx] = v;
         }
     }
@@ -624,6 +626,8 @@ ExpandParams expand_params(const Handle *h)
     E.Nx = static_cast<int>(h->c.Nx); E.Ny = static_cast<int>(h->c.Ny); E.Nz = static_cast<int>(h->c.Nz);
     E.sx = h->sx; E.sxy = h->sxy;
     E.xpp = h->xpp ? 1 : 0;
+    E.halo = h->order - 1;
+    E.pp1d = (h->dim == 1 && h->order == 4) ? 1 : 0;
     E.level_doubles = h->level_stride;
     E.g1 = -h->c.dt * h->c.dx_inv;
     return E;
@@ -667,6 +671,13 @@ int tail_init(Handle *h)
     double *il = tab.data() + nt;
     const int Ns[3] = {Nx, Ny, Nz};
     const double Linv[3] = {c.Lx_inv, c.Ly_inv, c.Lz_inv};
+    // B-spline basis at a node, N_i(0): the uniform-knot recurrence B_p[i] = ((t+p-i) B_{p-1}[i-1] + (1+i-t) B_{p-1}[i]) / p at t = 0
+    double nodal[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = 1; p < h->order; ++p) {
+        nodal[p] = 0.0;
+        for (int i = p - 1; i >= 1; --i) nodal[i] = ((p - i) * nodal[i - 1] + (1 + i) * nodal[i]) / p;
+        nodal[0] = nodal[0] / p;
+    }
     size_t off = 0;
     for (int d = 0; d < 3; ++d) {
         const int N = Ns[d];
@@ -674,16 +685,24 @@ int tail_init(Handle *h)
         for (int k = 0; k < N; ++k) {
             double ii = (2 * k < N) ? k : N - k; // folded wavenumber (poisson.cpp:76, 207-208, 345-347)
             kap[off + k] = (d < h->dim) ? ii * ii * fac * fac : 0.0;
-            // lambda(k) = (1 + 4 w + w^2)/6, w = exp(+2 pi i k/N): N_i(0) = (1/6, 4/6, 1/6, 0) (fields.hpp:76-79)
+            // lambda(k) = sum_i N_i(0) w^i, w = exp(+2 pi i k/N): the collocation stencil of fields.hpp:76-79 (cubic:
+            // N_i(0) = (1/6, 4/6, 1/6, 0), lambda = (1 + 4 w + w^2)/6)
             double lr = 1.0, li = 0.0;
             if (d < h->dim) {
                 const double th = 2 * M_PI * static_cast<double>(k) / N;
-                lr = (1.0 + 4.0 * std::cos(th) + std::cos(2 * th)) / 6.0;
-                li = (4.0 * std::sin(th) + std::sin(2 * th)) / 6.0;
+                lr = 0.0;
+                for (int i = 0; i < h->order; ++i) {
+                    lr += nodal[i] * std::cos(i * th);
+                    li += nodal[i] * std::sin(i * th);
+                }
             }
+            // odd orders on an even grid: lambda vanishes at the Nyquist mode (the stencil is symmetric about a half-integer) and
+            // the collocation system is singular; the reference's LSMR (started from zero) returns the minimum-norm least-squares
+            // solution, i.e. the pseudo-inverse: that mode of the coefficients is zero
             const double m2 = lr * lr + li * li;
-            il[2 * (off + k)] = lr / m2;
-            il[2 * (off + k) + 1] = -li / m2;
+            const bool null_mode = m2 < 1e-20;
+            il[2 * (off + k)] = null_mode ? 0.0 : lr / m2;
+            il[2 * (off + k) + 1] = null_mode ? 0.0 : -li / m2;
         }
         off += N;
     }
@@ -806,7 +825,7 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full, bool from_peer)
     NUFI_CUDA_CHECK(h, cudaGetLastError());
     if (cufftExecZ2D(h->plan_inv, h->d_spec, h->d_field) != CUFFT_SUCCESS)
         return fail(h, NUFI_B200_ERR_CUDA, "cufftExecZ2D failed");
-    if (h->dim == 1) {
+    if (E.pp1d) {
         expand1d_kernel<<<blocks_for(c.Nx + 3, 256, 64), 256, 0, h->stream>>>(h->d_field, h->d_raw + n * h->raw_stride, level, E,
                                                                           h->d_epart, sblocks, vol_half, h->d_energy + n);
     } else if (h->xpp) {
@@ -824,9 +843,9 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full, bool from_peer)
 }
 
 // Reference-format level (halo, row stride Nx+3) from periodic coefficients; 1 thread per output element.
-__global__ void expand_ref_kernel(const double *src, double *ref, int dim, int Nx, int Ny, int Nz)
+__global__ void expand_ref_kernel(const double *src, double *ref, int dim, int Nx, int Ny, int Nz, int halo)
 {
-    const int rx = Nx + 3, ry = dim >= 2 ? Ny + 3 : 1, rz = dim >= 3 ? Nz + 3 : 1;
+    const int rx = Nx + halo, ry = dim >= 2 ? Ny + halo : 1, rz = dim >= 3 ? Nz + halo : 1;
     const size_t total = static_cast<size_t>(rx) * ry * rz;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -884,7 +903,7 @@ int tail_filter(Handle *h, const double *d_values, int mode)
 int expand_field_to_stage(Handle *h)
 {
     expand_ref_kernel<<<blocks_for(h->stride_t, 256, 1184), 256, 0, h->stream>>>(h->d_field, h->d_stage, h->dim, static_cast<int>(h->c.Nx),
-                                                                               static_cast<int>(h->c.Ny), static_cast<int>(h->c.Nz));
+                                                                               static_cast<int>(h->c.Ny), static_cast<int>(h->c.Nz), h->order - 1);
     NUFI_CUDA_CHECK(h, cudaGetLastError());
     h->launches += 1;
     return NUFI_B200_OK;
@@ -900,7 +919,7 @@ int convert_level_to_device(Handle *h, size_t n, const double *d_ref_level)
                                                                                      h->d_raw + n * h->raw_stride, E, 0, nullptr, 0, 0.0, nullptr);
     else
     ref_to_device_kernel<<<blocks_for(h->level_stride, 256, 1184), 256, 0, h->stream>>>(
-        d_ref_level, h->d_hist + n * h->level_stride, h->dim == 1 ? h->d_raw + n * h->raw_stride : nullptr, E);
+        d_ref_level, h->d_hist + n * h->level_stride, E.pp1d ? h->d_raw + n * h->raw_stride : nullptr, E);
     NUFI_CUDA_CHECK(h, cudaGetLastError());
     h->launches += 1;
     return NUFI_B200_OK;

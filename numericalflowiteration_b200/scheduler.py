@@ -109,6 +109,12 @@ class CudaScheduler:
     def compute_metrics(self, n: int, q_begin: int, q_end: int) -> None:
         self._ck(self._L.nufi_b200_compute_metrics(self._h, n, q_begin, q_end))
 
+    def set_metrics_grid(self, conf_metrics=None) -> None:
+        """dim 1: integrate the metrics over the (x,u) grid of ``conf_metrics`` while the field stays on the grid of the
+        scheduler's own configuration -- the reference's ``cuda_scheduler(conf, conf_metrics)`` (cuda_scheduler.hpp:65-85,
+        cuda_kernel.cu:55-70).  ``None`` restores the scheduler's own grid."""
+        self._ck(self._L.nufi_b200_set_metrics_grid_1d(self._h, C.addressof(conf_metrics) if conf_metrics is not None else None))
+
     def download_metrics(self, metrics: np.ndarray) -> None:
         assert metrics.dtype == np.float64 and metrics.size == 4
         self._ck(self._L.nufi_b200_download_metrics(self._h, _ptr(metrics)))

@@ -728,9 +728,13 @@ double orc_poisson_3d(const orc_conf3d *cf, double *data)
 /* ------------------------------------------------------------------ fields.hpp interpolate
  * The collocation system (fields.hpp:76-95, 200-241, 370-421): sum_ii N_ii(0) c[(i+ii) mod N] = values[i]
  * per dimension (tensor product).  The reference solves it with LSMR to eps; here it is solved exactly,
- * dimension by dimension, with a dense LU of the N x N circulant matrix (deviation stated in the header). */
+ * dimension by dimension, with a dense LU of the N x N circulant matrix (deviation stated in the header).
+ * Odd orders on an even grid: the stencil N_ii(0) is symmetric about a half-integer, so its symbol vanishes at the
+ * Nyquist mode s_i = (-1)^i and the system is singular.  LSMR started from zero (lsmr.tpp) converges to the minimum-norm
+ * least-squares solution A^+ v; A being normal with the single null vector s, A^+ v = (A + s s^T / n)^{-1} (v - s (s.v)/n),
+ * which is what is factored / solved here in that case. */
 
-typedef struct { size_t n; double *lu; size_t *piv; } circ_lu;
+typedef struct { size_t n; double *lu; size_t *piv; int singular; } circ_lu;
 
 static circ_lu circ_factor(int order, size_t n)
 {
@@ -742,6 +746,10 @@ static circ_lu circ_factor(int order, size_t n)
     orc_bspline_basis(order, 0, 0.0, N0);
     for (size_t i = 0; i < n; ++i)
         for (int ii = 0; ii < order; ++ii) F.lu[i * n + (i + (size_t)ii) % n] += N0[ii];
+    F.singular = (order % 2 == 1) && (n % 2 == 0);
+    if (F.singular)
+        for (size_t i = 0; i < n; ++i)
+            for (size_t j = 0; j < n; ++j) F.lu[i * n + j] += (((i + j) & 1) ? -1.0 : 1.0) / (double)n;
     for (size_t k = 0; k < n; ++k) {
         size_t p = k;
         for (size_t r = k + 1; r < n; ++r)
@@ -767,6 +775,12 @@ static void circ_solve(const circ_lu *F, double *x, size_t stride, double *work)
 {
     const size_t n = F->n;
     for (size_t i = 0; i < n; ++i) work[i] = x[i * stride];
+    if (F->singular) { /* remove the Nyquist component of the right-hand side */
+        double a = 0;
+        for (size_t i = 0; i < n; ++i) a += (i & 1) ? -work[i] : work[i];
+        a /= (double)n;
+        for (size_t i = 0; i < n; ++i) work[i] -= (i & 1) ? -a : a;
+    }
     for (size_t k = 0; k < n; ++k) { /* whole rows were swapped while factoring: permute first */
         size_t p = F->piv[k];
         if (p != k) { double t = work[k]; work[k] = work[p]; work[p] = t; }

@@ -206,6 +206,12 @@ class Reference:
             getattr(L, f"ref_rho_sweep_{dim}d").argtypes = [_sz, _dp, _p, _sz, _sz, _dp]
             getattr(L, f"ref_interpolate_{dim}d").argtypes = [_dp, _dp, _p]
             getattr(L, f"ref_run_{dim}d").argtypes = [_p, _sz, _sz, _dp, _p, _p]
+        self.has_orders = hasattr(L, "ref_basis_order")
+        if self.has_orders:
+            L.ref_basis_order.argtypes = [_i, _i, _d, _dp]
+            for dim in (1, 2, 3):
+                getattr(L, f"ref_rho_sweep_order_{dim}d").argtypes = [_i, _sz, _dp, _p, _sz, _sz, _dp]
+                getattr(L, f"ref_interpolate_order_{dim}d").argtypes = [_i, _dp, _dp, _p]
         self.selectable = bool(L.ref_f0_selectable())
 
     def threads(self) -> int:
@@ -228,6 +234,28 @@ class Reference:
 
     def f0(self, conf, *xv):
         return getattr(self.lib, f"ref_f0_{conf.dim}d")(*[float(a) for a in xv])
+
+    # the reference templates at spline orders 3..8 (every driver runs 4; the library is generic)
+    def basis_order(self, order, der, x):
+        out = np.zeros(order)
+        assert self.lib.ref_basis_order(order, der, float(x), out) == 0
+        return out
+
+    def rho_order(self, conf, f0, order, n, coeffs, l_begin=0, l_end=None):
+        if f0 is not None:
+            self.set_f0(conf.dim, f0)
+        nn = _nodes(conf)
+        l_end = nn if l_end is None else l_end
+        rho = np.zeros(nn)
+        assert getattr(self.lib, f"ref_rho_sweep_order_{conf.dim}d")(order, n, np.ascontiguousarray(coeffs), C.addressof(conf),
+                                                                     l_begin, l_end, rho) == 0
+        return rho[l_begin:l_end] if (l_begin, l_end) != (0, nn) else rho
+
+    def interpolate_order(self, conf, order, values):
+        level = np.zeros(_stride(conf, order))
+        assert getattr(self.lib, f"ref_interpolate_order_{conf.dim}d")(order, level, np.ascontiguousarray(values, dtype=np.float64).ravel(),
+                                                                       C.addressof(conf)) == 0
+        return level
 
     def field(self, conf, level, pos, der=None):
         d = conf.dim

@@ -213,6 +213,61 @@ void ref_interpolate_3d(double *level, const double *values, const orc_conf3d *c
     nufi::dim3::interpolate<double, 4>(level, values, c);
 }
 
+/* ---- the same reference templates at the other spline orders they are written for (nufi/splines.hpp:39-110 is generic; the
+ *      reference's CUDA side instantiates 3..8, nufi/cuda_kernel.cu:191-203): pins the order-generic paths of the oracle. */
+#define REF_ORDER_SWITCH(order, CALL) \
+    switch (order) {                  \
+    case 3: { constexpr size_t O = 3; CALL; } break; \
+    case 4: { constexpr size_t O = 4; CALL; } break; \
+    case 5: { constexpr size_t O = 5; CALL; } break; \
+    case 6: { constexpr size_t O = 6; CALL; } break; \
+    case 7: { constexpr size_t O = 7; CALL; } break; \
+    case 8: { constexpr size_t O = 8; CALL; } break; \
+    default: return 1;                \
+    }
+
+int ref_basis_order(int order, int der, double x, double *out)
+{
+    REF_ORDER_SWITCH(order, if (der == 0) (nufi::splines1d::N<double, O, 0>(x, out)); else if (der == 1) (nufi::splines1d::N<double, O, 1>(x, out)); else (nufi::splines1d::N<double, O, 2>(x, out)))
+    return 0;
+}
+int ref_rho_sweep_order_1d(int order, size_t n, const double *coeffs, const orc_conf1d *cf, size_t l_begin, size_t l_end, double *rho)
+{
+    c1 c = to_ref<c1>(cf);
+    REF_ORDER_SWITCH(order, _Pragma("omp parallel for schedule(dynamic, 1)") for (size_t l = l_begin; l < l_end; ++l) rho[l] = (nufi::dim1::eval_rho<double, O>(n, l, coeffs, c)))
+    return 0;
+}
+int ref_rho_sweep_order_2d(int order, size_t n, const double *coeffs, const orc_conf2d *cf, size_t l_begin, size_t l_end, double *rho)
+{
+    c2 c = to_ref<c2>(cf);
+    REF_ORDER_SWITCH(order, _Pragma("omp parallel for schedule(dynamic, 1)") for (size_t l = l_begin; l < l_end; ++l) rho[l] = (nufi::dim2::eval_rho<double, O>(n, l, coeffs, c)))
+    return 0;
+}
+int ref_rho_sweep_order_3d(int order, size_t n, const double *coeffs, const orc_conf3d *cf, size_t l_begin, size_t l_end, double *rho)
+{
+    c3 c = to_ref<c3>(cf);
+    REF_ORDER_SWITCH(order, _Pragma("omp parallel for schedule(dynamic, 1)") for (size_t l = l_begin; l < l_end; ++l) rho[l] = (nufi::dim3::eval_rho<double, O>(n, l, coeffs, c)))
+    return 0;
+}
+int ref_interpolate_order_1d(int order, double *level, const double *values, const orc_conf1d *cf)
+{
+    c1 c = to_ref<c1>(cf);
+    REF_ORDER_SWITCH(order, (nufi::dim1::interpolate<double, O>(level, values, c)))
+    return 0;
+}
+int ref_interpolate_order_2d(int order, double *level, const double *values, const orc_conf2d *cf)
+{
+    c2 c = to_ref<c2>(cf);
+    REF_ORDER_SWITCH(order, (nufi::dim2::interpolate<double, O>(level, values, c)))
+    return 0;
+}
+int ref_interpolate_order_3d(int order, double *level, const double *values, const orc_conf3d *cf)
+{
+    c3 c = to_ref<c3>(cf);
+    REF_ORDER_SWITCH(order, (nufi::dim3::interpolate<double, O>(level, values, c)))
+    return 0;
+}
+
 /* The CPU drivers' time loop with the solve stage ported (FFTW absent): reference eval_rho ->
  * orc_poisson_* -> reference interpolate. */
 void ref_run_1d(const orc_conf1d *cf, size_t n_begin, size_t n_end, double *coeffs, double *energy, double *rho_out)

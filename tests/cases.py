@@ -37,6 +37,14 @@ CASES = {
 }
 
 
+# spline orders other than 4 (tests/golden/orders.npz): (config, f0, history levels); every N_d >= 8 = the largest order
+ORDER_CASES = {
+    "1d": (lambda: conf1d(Nx=32, Nu=24, Nt=12), F0(1, 0.01, 0.5), 12),
+    "2d": (lambda: conf2d(Nx=10, Ny=9, Nu=6, Nv=5, Nt=8), F0(0, 0.05, 0.5), 8),
+    "3d": (lambda: conf3d(Nx=8, Ny=9, Nz=8, Nu=3, Nv=4, Nw=3, Nt=6), F0(0, 0.001, 0.2), 6),
+}
+
+
 def rel_linf(a, b):
     import numpy as np
 

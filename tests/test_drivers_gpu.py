@@ -57,6 +57,94 @@ def test_driver_energy_trace(dim, steps, mode, oracle, tmp_path):
         assert abs(first[1] - conf_volume(conf)) <= 1e-3 * conf_volume(conf) or dim == 3  # L1 norm = int f = box volume (1d, 2d weights)
 
 
+def _csv_rows(path):
+    rows = open(path).read().strip().splitlines()
+    assert rows[0].startswith('"Time"; "L1-Norm"; "L2-Norm"; "Electric Energy"; "Kinetic Energy"; "Total Energy"; "Entropy"')
+    return np.array([[float(x) for x in r.split(";")] for r in rows[1:]])
+
+
+@pytest.mark.parametrize("dim,steps", [(1, 12), (2, 6), (3, 8)])
+def test_statistics_csv_numeric_rows(dim, steps, oracle, tmp_path):
+    """statistics.csv of the GPU drivers (bin/test_nufi_gpu_2d.cpp:119-121, 225-246): every numeric row -- time, L1, L2 (square
+    root taken), electric / kinetic / total energy, entropy -- against the oracle's metrics of the same run.  The file carries 7
+    significant digits (std::scientific, default precision, as the reference writes it)."""
+    conf, f0 = landau_conf(dim, steps)
+    coeffs, energy, _ = oracle.run(conf, f0, steps + 1)
+    _, _, cwd = run_driver(f"test_nufi_gpu_{dim}d", ["--landau", "--steps", str(steps), "--fused"], tmp_path)
+    rows = _csv_rows(cwd / "statistics.csv")
+    assert len(rows) == steps + 1
+    from numericalflowiteration_b200 import n_quad
+
+    for n in (0, 1, steps // 2, steps):
+        m = oracle.metrics(conf, f0, n, coeffs, 0, n_quad(conf))
+        want = [n * conf.dt, m[0], np.sqrt(m[1]), energy[n], m[2], m[2] + energy[n], m[3]]
+        assert np.allclose(rows[n], want, rtol=2e-6, atol=1e-300), (dim, n, rows[n], want)
+
+
+def test_stats_txt_of_the_1d_cpu_driver(oracle, tmp_path):
+    """stats.txt and E_<t>.txt of bin/test_nufi_cpu_1d.cpp:82-119: every second step "t  max|E|  sum E^2 * dx" over 256 plot
+    points (widths 20, 8 digits), every 160th step the samples themselves."""
+    steps = 12
+    conf, f0 = landau_conf(1, steps)
+    coeffs, _, _ = oracle.run(conf, f0, steps + 1)
+    _, _, cwd = run_driver("test_nufi_cpu_1d", ["--landau", "--steps", str(steps)], tmp_path)
+    lines = open(cwd / "stats.txt").read().splitlines()
+    assert len(lines) == steps // 2 + 1 and all(len(ln) == 60 for ln in lines)
+    st = stride_t(conf)
+    xs = [conf.x_min + i * (conf.Lx / 256) for i in range(256)]
+    for row, ln in enumerate(lines):
+        n = 2 * row
+        E = np.array([-oracle.field(conf, coeffs[n * st:(n + 1) * st], (x,), (1,)) for x in xs])
+        want = [n * conf.dt, np.max(np.abs(E)), np.sum(E * E) * conf.dx]
+        assert np.allclose([float(v) for v in ln.split()], want, rtol=5e-8, atol=1e-300), (n, ln, want)
+    e0 = np.loadtxt(cwd / "E_0.000000.txt")
+    assert e0.shape == (256, 2) and np.allclose(e0[:, 0], xs, rtol=1e-5)
+
+
+def test_gpu_1d_driver_with_a_separate_metrics_grid(oracle, tmp_path):
+    """The reference's 1d GPU driver builds its scheduler from two configs (bin/test_nufi_gpu_1d.cpp:216-230); with a metrics
+    grid finer than the field grid the L1 norm (the integral of f over phase space) must still be the box volume."""
+    steps = 6
+    conf, f0 = landau_conf(1, steps)
+    _, want, _ = oracle.run(conf, f0, steps)
+    got, _, cwd = run_driver("test_nufi_gpu_1d", ["--landau", "--steps", str(steps), "--metrics-grid", "384", "640"], tmp_path)
+    assert np.max(np.abs(got[:steps] - want) / np.abs(want)) <= ENERGY_TOL
+    rows = _csv_rows(cwd / "statistics.csv")
+    assert np.allclose(rows[:, 1], conf.Lx, rtol=1e-5)
+
+
+REF_DRV = os.path.join(ROOT, "oracle", "_ref", "drivers")
+REF_GPU_3D = os.path.join(REF_DRV, "ref_test_nufi_gpu_3d")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GPU_3D), reason="oracle/_ref/drivers/ref_* are built by __graft_entry__.build() where /root/reference exists")
+def test_unmodified_reference_gpu_3d_driver_runs_on_the_library(oracle, tmp_path):
+    """The reference's OWN bin/test_nufi_gpu_3d.cpp, compiled unmodified against include/ (see tests/test_host_cpu.py), run on the
+    GPU through libnufi_b200: its statistics.csv (as-committed 3d configuration: 8^3 x 8^3, bump-on-tail, Nt = 50, u in [-9,0])
+    against the oracle's run of the same configuration."""
+    r = subprocess.run([REF_GPU_3D], capture_output=True, text=True, cwd=tmp_path, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rows = _csv_rows(tmp_path / "statistics.csv")
+    conf, f0 = Config3D(), F0(2, 0.03, 0.3)
+    assert len(rows) == conf.Nt + 1
+    coeffs, energy, _ = oracle.run(conf, f0, conf.Nt + 1)
+    assert np.allclose(rows[:, 3], energy, rtol=2e-6)
+    from numericalflowiteration_b200 import n_quad
+
+    for n in (0, 7, conf.Nt):
+        m = oracle.metrics(conf, f0, n, coeffs, 0, n_quad(conf))
+        assert np.allclose(rows[n, [1, 2, 4, 6]], [m[0], np.sqrt(m[1]), m[2], m[3]], rtol=2e-6), (n, rows[n], m)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_DRV, "ref_test_nufi_cpu_3d")), reason="oracle/_ref/drivers/ref_* not built")
+def test_unmodified_reference_cpu_3d_driver_runs_on_the_library(tmp_path):
+    """bin/test_nufi_cpu_3d.cpp unmodified: the OpenMP loop over eval_rho(n, l, coeffs, conf), poisson::solve, interpolate --
+    every call served by the device library.  It prints timings only; the run must complete all Nt = 50 steps."""
+    r = subprocess.run([os.path.join(REF_DRV, "ref_test_nufi_cpu_3d")], capture_output=True, text=True, cwd=tmp_path, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "n = 49 " in r.stdout and "Total time:" in r.stdout
+
+
 def conf_volume(conf):
     v = conf.Lx
     if conf.dim >= 2:

@@ -102,10 +102,15 @@ def test_no_cpu_fallback_fails_loudly():
 
 
 def test_argument_errors_do_not_need_a_gpu():
-    with pytest.raises(ValueError):
-        CudaScheduler(conf2d(), F0(0, 0.05, 0.5), order=3)
+    for bad_order in (2, 9):  # the reference instantiates orders 3..8 (nufi/cuda_kernel.cu:191-203)
+        with pytest.raises(ValueError):
+            CudaScheduler(conf2d(), F0(0, 0.05, 0.5), order=bad_order)
     with pytest.raises(ValueError):
         CudaScheduler(conf2d(Nx=2), F0(0, 0.05, 0.5))
+    with pytest.raises(ValueError):  # grid smaller than the spline window
+        CudaScheduler(conf2d(Nx=5), F0(0, 0.05, 0.5), order=6)
+    with pytest.raises(ValueError, match="not periodic"):  # f0 must have the period of the box (k L = 2 pi m)
+        CudaScheduler(conf2d(), F0(0, 0.05, 0.37))
 
 
 _WORKER = r'''
@@ -178,6 +183,71 @@ def test_cpp_drivers_build_and_fail_loudly_without_gpu():
         r = subprocess.run([os.path.join(ROOT, "bin", "build", name), "--steps", "1"], capture_output=True, text=True, timeout=120)
         assert r.returncode != 0
         assert "error:" in r.stderr and ("CUDA" in r.stderr or "cuda" in r.stderr)
+
+
+REF_BIN = "/root/reference/bin"
+REF_DRIVERS = ["test_nufi_cpu_1d", "test_nufi_cpu_2d", "test_nufi_cpu_3d", "test_nufi_gpu_2d", "test_nufi_gpu_3d"]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_BIN), reason="needs the reference checkout (build container only)")
+@pytest.mark.parametrize("name", REF_DRIVERS)
+def test_unmodified_reference_drivers_compile_against_include(name):
+    """INTEGRATION.md section A, literally: the reference's OWN driver sources, unmodified and read where they lie, compile and
+    link with -I<repo>/include ALONE (no reference include path behind it, no nvcc, FFTW, BLAS or MPI) against libnufi_b200.so.
+    (bin/test_nufi_gpu_1d.cpp needs Armadillo for its SVD post-processing -- out of scope -- and is not in the list.)
+    __graft_entry__.build() leaves the same binaries in oracle/_ref/drivers/ref_* so the GPU suite can run them."""
+    out = os.path.join(ROOT, "oracle", "_ref", "drivers", "ref_" + name)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-fopenmp", "-I" + os.path.join(ROOT, "include"), os.path.join(REF_BIN, name + ".cpp"),
+                        "-o", out, "-L" + os.path.dirname(_lib.LIB_PATH), "-lnufi_b200", "-Wl,-rpath,$ORIGIN/../../../numericalflowiteration_b200/lib",
+                        "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    if not _has_gpu():  # no silent CPU path behind the reference's own loop either
+        rr = subprocess.run([out], capture_output=True, text=True, timeout=120, cwd=os.path.dirname(out))
+        assert rr.returncode != 0 and ("CUDA" in rr.stderr or "cuda" in rr.stderr), rr.stderr[-500:]
+
+
+def test_host_eval_any_order_and_derivative(tmp_path, oracle):
+    """include/nufi/fields.hpp eval<real,order,dx[,dy,dz]> -- the host-side spline evaluation the drivers use for plots, generic
+    in order and derivative like the reference's (nufi/fields.hpp:36-61; bin/test_nufi_gpu_1d.cpp:301 uses dx = 2) -- against
+    the oracle's restatement of splines.hpp / fields.hpp (itself pinned bit for bit by tests/golden/orders.npz)."""
+    src = r'''
+#include <nufi/fields.hpp>
+#include <cstdio>
+#include <vector>
+template <size_t O> void run(const std::vector<double>& l1, const std::vector<double>& l2) {
+  nufi::dim1::config_t<double> a; a.Nx = 12; a.x_min = -1.0; a.x_max = 5.0; a.derive();
+  nufi::dim2::config_t<double> b; b.Nx = 9; b.Ny = 8; b.y_min = 0.5; b.y_max = 7.0; b.derive();
+  const double xs[3] = {-3.3, 0.2, 4.9999}, ys[3] = {0.1, 3.0, 9.7};
+  for (int i = 0; i < 3; ++i) {
+    std::printf("%.17g %.17g %.17g ", nufi::dim1::eval<double,O,0>(xs[i], l1.data(), a), nufi::dim1::eval<double,O,1>(xs[i], l1.data(), a),
+                nufi::dim1::eval<double,O,2>(xs[i], l1.data(), a));
+    std::printf("%.17g %.17g %.17g %.17g\n", nufi::dim2::eval<double,O,0,0>(xs[i], ys[i], l2.data(), b), nufi::dim2::eval<double,O,1,0>(xs[i], ys[i], l2.data(), b),
+                nufi::dim2::eval<double,O,0,1>(xs[i], ys[i], l2.data(), b), nufi::dim2::eval<double,O,1,1>(xs[i], ys[i], l2.data(), b));
+  }
+}
+int main() {
+  std::vector<double> l1(12 + 7), l2((9 + 7) * (8 + 7));
+  for (size_t i = 0; i < l1.size(); ++i) l1[i] = 0.3 + 0.01 * double((i * 7919) % 101);
+  for (size_t i = 0; i < l2.size(); ++i) l2[i] = -0.2 + 0.01 * double((i * 104729) % 97);
+  run<3>(l1, l2); run<4>(l1, l2); run<5>(l1, l2); run<6>(l1, l2); run<8>(l1, l2);
+  return 0; }'''
+    (tmp_path / "t.cpp").write_text(src)
+    subprocess.run(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-o", str(tmp_path / "t"), str(tmp_path / "t.cpp"),
+                    "-L", os.path.dirname(_lib.LIB_PATH), "-lnufi_b200", "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH)], check=True)
+    rows = [[float(v) for v in ln.split()] for ln in subprocess.run([str(tmp_path / "t")], capture_output=True, text=True, check=True).stdout.splitlines()]
+    a = Config1D(Nx=12, x_min=-1.0, x_max=5.0)
+    b = Config2D(Nx=9, Ny=8, y_min=0.5, y_max=7.0)
+    l1 = np.array([0.3 + 0.01 * ((i * 7919) % 101) for i in range(19)])
+    l2 = np.array([-0.2 + 0.01 * ((i * 104729) % 97) for i in range(16 * 15)])
+    xs, ys = [-3.3, 0.2, 4.9999], [0.1, 3.0, 9.7]
+    k = 0
+    for order in (3, 4, 5, 6, 8):
+        for i in range(3):
+            want = [oracle.field(a, l1, (xs[i],), (d,), order=order) for d in (0, 1, 2)]
+            want += [oracle.field(b, l2, (xs[i], ys[i]), d, order=order) for d in ((0, 0), (1, 0), (0, 1), (1, 1))]
+            assert np.allclose(rows[k], want, rtol=1e-12, atol=1e-13), (order, i, rows[k], want)
+            k += 1
 
 
 def test_reference_layout_header_compiles_as_cxx():

@@ -165,3 +165,43 @@ def test_phase_flow_bit_exact(oracle):
         got = oracle.phase_flow(conf, int(n), g["coeffs"], pf["pts"])
         assert np.array_equal(got, want), int(n)
     assert np.array_equal(pf["feet"][0][:, 1], pf["pts"][:, 1]) and np.array_equal(pf["feet"][1][:, 1], pf["pts"][:, 1])  # n <= 1: u untouched
+
+
+# ------------------------------------------------------------------ spline orders other than 4 (tests/golden/orders.npz)
+@pytest.mark.parametrize("order", [3, 5, 6, 8])
+def test_generic_order_golden(order, oracle):
+    """The reference is generic in the spline order (nufi/splines.hpp:39-110) and instantiates its kernels for 3..8
+    (nufi/cuda_kernel.cu:191-203).  Vectors from the REAL reference templates at orders 3, 5, 6, 8
+    (tests/golden/make_order_golden.py): basis values/derivatives and teacher-forced rho bit for bit, interpolate to LSMR's
+    tolerance -- including odd orders on even grids, where the collocation system is singular and LSMR returns the
+    minimum-norm least-squares solution."""
+    from cases import ORDER_CASES
+
+    g = np.load(os.path.join(HERE, "golden", "orders.npz"))
+    for der in (0, 1, 2):
+        for x, want in zip(g["xs"], g[f"basis_o{order}"][der]):
+            assert np.array_equal(oracle.basis(order, der, x), want), (order, der, x)
+    for name, (mk, f0, n_lev) in ORDER_CASES.items():
+        conf = mk()
+        coeffs = g[f"coeffs_{name}_o{order}"]
+        for n, want in zip(g[f"steps_{name}_o{order}"], g[f"rho_{name}_o{order}"]):
+            got = oracle.rho(conf, f0, int(n), coeffs, order=order)
+            assert np.array_equal(got, want), (name, order, int(n), np.max(np.abs(got - want)))
+        level = oracle.interpolate(conf, g[f"rho_{name}_o{order}"][-1], order=order)
+        assert rel_linf(level, g[f"level_{name}_o{order}"]) <= 1e-11, (name, order)
+
+
+@pytest.mark.parametrize("order", [3, 5, 7])
+def test_generic_order_live_reference(order, oracle, reference):
+    """Same check against the reference compiled here (orders beyond the committed vectors included)."""
+    from cases import ORDER_CASES
+
+    if not reference.has_orders:
+        pytest.skip("oracle/_ref built before the order-generic entry points existed")
+    for name, (mk, f0, n_lev) in ORDER_CASES.items():
+        conf = mk()
+        coeffs, _, _ = oracle.run(conf, f0, n_lev, order=order)
+        assert np.isfinite(coeffs).all()
+        want = reference.rho_order(conf, f0, order, n_lev, coeffs)
+        assert np.array_equal(oracle.rho(conf, f0, n_lev, coeffs, order=order), want), (name, order)
+        assert rel_linf(oracle.interpolate(conf, want, order=order), reference.interpolate_order(conf, order, want)) <= 1e-11
