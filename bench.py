@@ -5,16 +5,22 @@ A *step* is one NuFI time step at a fixed history depth n: trace every quadratur
 levels, f0 at the foot, reduce into rho, Poisson + spline interpolation into level n -- all on the device, through
 the C ABI of libnufi_b200.so.  One step costs Nquad * n point-steps.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C1|C2|C3|C4|C5-16|C5-32] [--depth n]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C1|C2|C3|C4|C5-16|C5-32] [--depth n] [--scaling weak|strong]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1: one rank per GPU)
     python bench.py --impl reference ...      the reference's own CPU eval_rho (oracle/_ref) on the host cores
 
-Only the cpu_baseline leg and --impl reference execute anything under oracle/ (as the measured CPU baseline and as
+The JSON line carries, beside the contract's keys: `parity` (live rho check against the reference's CPU eval_rho on the same
+history, at every N; N > 1 adds a checksum proving all replicas hold bit-identical rho and level n), `other_workloads`
+(1d/2d/3d at N = 1; the 3d configurations of BASELINE.json in STRONG and weak form at N > 1, each with its own parity),
+`full_run` (complete free runs, N = 1).
+
+Only the cpu_baseline / parity legs and --impl reference execute anything under oracle/ (as the measured CPU baseline and as
 the live parity check); the GPU numbers never touch it.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import math
 import os
@@ -30,19 +36,20 @@ if ROOT not in sys.path:
 
 FLOP_PER_POINT_STEP = {1: 30.0, 2: 138.0, 3: 431.0}  # SURVEY.md section 8d / App. A.4 (algorithmic, FMA = 2)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE backtrace launch at the default depth, from the committed ncu --set full
-# captures (profiles/r01c_ncu_full_summary.csv); the algorithmic figure is n*level_bytes + 16*Nnodes
-NCU_DRAM_TRAFFIC_BYTES = {"C2": 4.98e6, "C3": 3.65e6, "C4": 1.62e6, "C5-16": 1.44e6}
+# captures (profiles/r01c_ncu_full_summary.csv, profiles/r02a_ncu_C5-32.csv); the algorithmic figure is n*level_bytes + 16*Nnodes
+NCU_DRAM_TRAFFIC_BYTES = {"C2": 4.98e6, "C3": 3.65e6, "C4": 1.62e6, "C5-16": 1.44e6, "C5-32": 8.73e6}
 SMEM_BYTES_PER_POINT_STEP = {1: 24.0, 2: 128.0, 3: 512.0}  # coefficients a point gathers per level
 SMEM_BYTES_PER_CLK_SM = 128.0  # shared-memory data pipe; tools/microbench.cu measures 125-127 on this GPU
 L2_FLUSH_BYTES = 256 << 20
+RHO_TOL = 1e-10
 
 
-def make_workload(name: str, n_gpus: int):
-    """(conf, f0, depth n, description).  Weak scaling: the velocity quadrature grows with the GPU count so the
-    quadrature points per GPU stay fixed (BASELINE.json configs[4]: 'larger Nx and Nv quadrature')."""
+def make_workload(name: str, n_gpus: int, scaling: str = "weak"):
+    """(conf, f0, depth n, description).  weak: the velocity quadrature grows with the GPU count so the quadrature points per
+    GPU stay fixed (BASELINE.json configs[4]: 'larger Nx and Nv quadrature'); strong: the grid BASELINE names, whatever N."""
     from numericalflowiteration_b200 import Config1D, Config2D, Config3D, F0
 
-    g = max(n_gpus, 1)
+    g = max(n_gpus, 1) if scaling == "weak" else 1
     if name in ("C1", "C2"):
         conf = Config1D(Nu=512 * g)  # 256 x 512, dt = 1/16, Nt = 1600 (nufi/config.hpp:58-65)
         f0 = F0(0, 0.01, 0.5) if name == "C1" else F0(1, 0.01, 0.5)
@@ -118,17 +125,29 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def reference_sweep_timer(conf, f0, n, coeffs, budget_s: float):
-    """Times the reference's own OpenMP rho sweep (oracle/_ref, -O3 AVX2+FMA build; falls back to the C port) on a
-    bounded sample of spatial nodes.  Returns (callable running one sample -> seconds, point-steps per sample,
-    description, kind, threads, rho of the sample nodes)."""
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        return os.cpu_count() or 1
+
+
+def reference_impl():
+    """The reference's own OpenMP rho sweep (oracle/_ref, -O3 AVX2+FMA build; the C port when oracle/_ref is absent), with the
+    OpenMP thread count set EXPLICITLY to the host's cores (torchrun exports OMP_NUM_THREADS=1 to every rank)."""
     from oracle.oracle_py import Oracle, Reference
+
+    impl = Reference("_fast") if Reference.available("_fast") else Oracle(fast=True)
+    impl.set_threads(host_cores())
+    return impl
+
+
+def reference_sweep_timer(conf, f0, n, coeffs, budget_s: float, impl=None):
+    """Times the reference sweep on a bounded sample of spatial nodes.  Returns (callable running one sample -> seconds,
+    point-steps per sample, description, kind, threads, nodes in the sample, dict receiving rho of the sample nodes)."""
     from numericalflowiteration_b200 import n_nodes, n_vel
 
-    if Reference.available("_fast"):
-        impl = Reference("_fast")
-    else:
-        impl = Oracle(fast=True)
+    impl = impl or reference_impl()
     nn, nv = n_nodes(conf), n_vel(conf)
     threads = impl.threads()
     # calibrate on a few nodes, then size the sample for the budget
@@ -152,6 +171,35 @@ def reference_sweep_timer(conf, f0, n, coeffs, budget_s: float):
     return run, float(l_n) * nv * max(n, 1), desc, impl.kind, threads, l_n, out
 
 
+def reference_history(name: str, n: int):
+    """The history the reference arm's timed step reads: the reference CPU loop's own free run of the workload's BASE grid
+    (what the GPU arm builds on the device, to parity tolerance), computed once with all host cores and cached under /tmp; for
+    workloads whose CPU free run would take more than a few minutes (C3, C5) a synthetic smooth history instead."""
+    from numericalflowiteration_b200 import n_quad
+    from oracle.oracle_py import Oracle, synthetic_history
+
+    conf, f0, _, _ = make_workload(name, 1)
+    cost = float(n_quad(conf)) * n * (n - 1) / 2
+    if cost > 6e10:
+        return synthetic_history(conf, n, seed=1234, amp=1e-2), "synthetic smooth sine potentials (numpy), seed 1234 (a CPU free run would take too long)"
+    cache = f"/tmp/nufi_b200_refhist_{name}_{n}.npy"
+    if os.path.exists(cache):
+        try:
+            return np.load(cache), f"free run of the reference CPU loop on the base grid to depth {n} (cached: {cache})"
+        except Exception:  # noqa: BLE001
+            pass
+    orc = Oracle(fast=True)
+    orc.set_threads(host_cores())
+    t0 = time.perf_counter()
+    coeffs, _, _ = orc.run(conf, f0, n)
+    dt = time.perf_counter() - t0
+    try:
+        np.save(cache, coeffs)
+    except Exception:  # noqa: BLE001
+        pass
+    return coeffs, f"free run of the reference CPU loop on the base grid to depth {n} ({dt:.0f} s on {orc.threads()} threads, untimed)"
+
+
 def reference_cuda_leg(conf, f0, n, coeffs_host, sched, device, reps=3):
     """Informational (north star: 'the reference's existing CUDA path'): the reference's own nufi/cuda_kernel.cu, compiled
     unmodified for sm_100a (oracle/_ref/libnufi_refcuda.so), timed with CUDA events on the same GPU, same history, same step.
@@ -168,9 +216,9 @@ def reference_cuda_leg(conf, f0, n, coeffs_host, sched, device, reps=3):
         rc.close()
         out = {"value": float(n_quad(conf)) * n / (ms * 1e-3), "unit": "point-steps/s", "kernel_ms": ms, "reps": reps,
                "what": "reference nufi/cuda_kernel.cu (cuda_kernel<double,4>::compute_rho: memset + cuda_eval_rho, 64-thread blocks, "
-                       "atomicAdd), compiled unmodified for sm_100a, CUDA-event timed on this GPU at the same depth"}
+                       "atomicAdd), compiled unmodified for sm_100a, CUDA-event timed on ONE GPU at the same depth"}
         same_f0 = conf.dim == 1 and f0.kind == 1 and list(f0.p)[:2] == [0.01, 0.5]
-        if same_f0:
+        if same_f0 and sched is not None:
             ours = sched.eval_rho(n)
             out["rho_rel_linf_ours_vs_reference_cuda"] = float(np.max(np.abs(ours - rho)) / np.max(np.abs(rho)))
         return out
@@ -182,11 +230,9 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    from oracle.oracle_py import synthetic_history
-
-    conf, f0, depth, desc = make_workload(args.workload, args.gpus)
+    conf, f0, depth, desc = make_workload(args.workload, args.gpus, args.scaling)
     n = args.depth or depth
-    coeffs = synthetic_history(conf, n, seed=1234, amp=1e-2)
+    coeffs, hist_desc = reference_history(args.workload, n)
     total = max(args.steps + args.warmup, 1)
     budget = min(2.0, max(0.05, 90.0 / total))
     run, psteps, sdesc, kind, threads, _, _ = reference_sweep_timer(conf, f0, n, coeffs, budget)
@@ -198,8 +244,8 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": "backtrace point-steps/sec", "value": value, "unit": "point-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "depth_n": n, "history": "synthetic smooth sine potentials (numpy), seed 1234"},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "depth_n": n, "history": hist_desc, "host_cores": host_cores(), "omp_threads": threads},
         "cpu_baseline": {"value": value, "unit": "point-steps/s", "cores": threads, "kind": kind, "sample": sdesc},
         "e2e": {"value": value, "unit": "point-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -209,7 +255,7 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 class GpuRunner:
-    """One rank's scheduler + (for N > 1) the NCCL all-reduce of the partial rho."""
+    """One rank's scheduler + (for N > 1) the exchange of the partial rho: peer memory fused into the kernels, or NCCL."""
 
     def __init__(self, conf, f0, rank, world, torch, dist, exchange="peer"):
         from numericalflowiteration_b200 import CudaScheduler, partition
@@ -258,6 +304,18 @@ class GpuRunner:
             with self.torch.cuda.stream(self.stream):
                 self.dist.all_reduce(self.rho_t, op=self.dist.ReduceOp.SUM)
             self.s.field_tail_device(n, self.rho_t.data_ptr())
+
+    def my_point_steps(self, n):
+        """Point-steps this rank's backtrace kernel traces in one step at depth n."""
+        if self.world > 1 and self.exchange == "peer-memory":  # velocity nodes rank, rank+world, ... of every spatial node
+            return float(self.s.n_nodes) * len(range(self.rank, self.s.n_quad // self.s.n_nodes, self.world)) * n
+        return float(self.q1 - self.q0) * n
+
+    def close(self):
+        self.stream.synchronize()
+        if self.world > 1:
+            self.dist.barrier()  # every rank is done with every peer's exchange buffer
+        self.s.close()
 
 
 def timed_region(runner, n, steps, warmup, flush, torch, dist, sampler=None):
@@ -370,6 +428,132 @@ def free_run(runner, n_levels):
     runner.stream.synchronize()
 
 
+def download_history(s, n):
+    from numericalflowiteration_b200 import stride_t
+
+    st_ = stride_t(s.conf)
+    out = np.zeros((n + 1) * st_)
+    for lvl in range(n):
+        out[lvl * st_:(lvl + 1) * st_] = s.download_phi(lvl)
+    return out
+
+
+def live_parity(runner, conf, f0, n, coeffs_host, cpu_budget, dist, want_cpu_baseline):
+    """The rho the last fused step at depth n consumed (N > 1: the sum over all ranks' shares, exchanged through peer memory
+    or NCCL -- nufi_b200_download_rho_full) against the reference's CPU eval_rho on the same history, on a sample of spatial
+    nodes (rank 0); N > 1: plus SHA-256 of rho and of level n gathered from every rank -- the replicas must be bit-identical.
+    Returns (parity dict, cpu_baseline dict or None) on rank 0, (None, None) elsewhere.  Collective: every rank calls it."""
+    s = runner.s
+    got = s.download_rho_full()
+    replicas = None
+    if runner.world > 1:
+        level = s.download_phi(n)
+        digest = hashlib.sha256(got.tobytes()).hexdigest()[:16] + ":" + hashlib.sha256(level.tobytes()).hexdigest()[:16]
+        all_d = [None] * runner.world
+        dist.all_gather_object(all_d, digest)
+        replicas = {"bit_identical": len(set(all_d)) == 1, "sha256_rho:level_n": sorted(set(all_d)), "ranks": runner.world}
+    parity = cpu = None
+    if runner.rank == 0:
+        run, cpu_psteps, sdesc, kind, threads, l_n, out = reference_sweep_timer(conf, f0, n, coeffs_host, cpu_budget)
+        t_cpu = run()
+        if want_cpu_baseline:
+            t_cpu = min(t_cpu, run())
+            cpu = {"value": cpu_psteps / t_cpu, "unit": "point-steps/s", "cores": threads, "kind": kind, "sample": sdesc, "seconds": t_cpu}
+        want = out["rho"][:l_n]
+        err = float(np.max(np.abs(got[:l_n] - want)) / np.max(np.abs(want)))
+        parity = {"rho_rel_linf_vs_cpu_reference": err, "nodes_checked": int(l_n), "tolerance": RHO_TOL, "ok": bool(err <= RHO_TOL),
+                  "what": "rho of the timed fused step (all ranks' shares summed) vs the reference CPU eval_rho on the downloaded history"}
+        if replicas is not None:
+            parity["replicas"] = replicas
+            parity["ok"] = bool(parity["ok"] and replicas["bit_identical"])
+    if runner.world > 1:
+        dist.barrier()
+    return parity, cpu
+
+
+def measure_workload(name, scaling, rank, world, local, args, flush, torch, dist, peak_tf, steps, with_ref_cuda, cpu_budget):
+    """One workload end to end on all ranks: history by free-running fused steps, the two timed regions, live parity.
+    Returns a dict on rank 0, None elsewhere."""
+    from numericalflowiteration_b200 import n_quad
+
+    conf, f0, depth, desc = make_workload(name, world, scaling)
+    r = GpuRunner(conf, f0, rank, world, torch, dist, exchange=args.exchange)
+    try:
+        free_run(r, depth)
+        m = measure_gpu(r, depth, steps, 3, flush, torch, dist)
+        if r.exchange == "peer-memory" and r.s.peer_timed_out():
+            raise RuntimeError("a wait for a peer's rho flag timed out")
+        ps = float(n_quad(conf)) * depth
+        ex = None
+        hist = download_history(r.s, depth) if (rank == 0 and not args.no_cpu) else None
+        parity = None
+        if not args.no_cpu:
+            parity, _ = live_parity(r, conf, f0, depth, hist, cpu_budget, dist, False)
+        if rank == 0:
+            tf = r.my_point_steps(depth) * FLOP_PER_POINT_STEP[conf.dim] / (m["bt_ms"] * 1e-3) / 1e12
+            ex = {"workload": desc, "scaling": scaling if world > 1 else None, "depth_n": depth, "n_quad": n_quad(conf),
+                  "point_steps_per_s": ps * steps / (m["t_ms"] * 1e-3), "ms_per_step": m["t_ms"] / steps, "steps": steps,
+                  "kernel_ms": m["bt_ms"], "kernel_ms_per_rank": m["bt_ms_per_rank"], "variant": r.s.last_variant, "exchange": r.exchange,
+                  "fp64_tflops_per_gpu": tf, "fp64_frac": tf / peak_tf, "parity": parity}
+            if with_ref_cuda and not args.no_cpu:
+                rc = reference_cuda_leg(conf, f0, depth, hist, None, local, reps=1 if (conf.dim == 3 and conf.Nx >= 32) else 2)
+                ex["reference_cuda_point_steps_per_s"] = rc.get("value")
+                ex["reference_cuda_kernel_ms"] = rc.get("kernel_ms")
+                if rc.get("value"):
+                    ex["speedup_vs_reference_cuda_one_gpu"] = ex["point_steps_per_s"] / rc["value"]
+        if world > 1:
+            dist.barrier()
+        return ex
+    finally:
+        r.close()
+
+
+def full_runs(args, torch, flush):
+    """Complete free runs on one GPU (what the reference's drivers print: total wall time and s per time step,
+    bin/test_nufi_cpu_2d.cpp:65-78, 104): C1 and C2 all 1600 steps, C4 all 50, through the fused step, host-timed from the
+    first launch to the final synchronisation; the electric-energy trace against the reference CPU run's
+    (tests/golden/fullsize_*.npz, made by tests/golden/make_fullsize_traces.py) over the window where the problem is well
+    conditioned (tests/test_fullsize_gpu.py gates the whole trace)."""
+    out = []
+    windows = {"C1": 500, "C2": 800, "C4": 50}
+    for name in ("C1", "C2", "C4"):
+        try:
+            conf, f0, _, desc = make_workload(name, 1)
+            r = GpuRunner(conf, f0, 0, 1, torch, None)
+            nt = int(conf.Nt)
+            for m in range(min(nt, 8)):  # warm: module load, first-launch costs
+                r.step(m)
+            r.stream.synchronize()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for m in range(nt + 1):
+                r.step(m)
+            r.stream.synchronize()
+            wall = time.perf_counter() - t0
+            e = r.s.download_energy(0, nt + 1)
+            from numericalflowiteration_b200 import n_quad
+
+            row = {"workload": desc, "time_steps": nt + 1, "wall_s": wall, "mean_s_per_time_step": wall / (nt + 1),
+                   "point_steps": float(n_quad(conf)) * nt * (nt + 1) / 2, "point_steps_per_s": float(n_quad(conf)) * nt * (nt + 1) / 2 / wall,
+                   "launches": 2 * (nt + 1)}
+            gpath = os.path.join(ROOT, "tests", "golden", f"fullsize_{name}.npz")
+            if os.path.exists(gpath):
+                g = np.load(gpath)
+                ref_e = np.asarray(g["energy"], dtype=np.float64)
+                w = min(windows[name], len(ref_e), len(e))
+                row["energy_trace_rel_err"] = float(np.max(np.abs(e[:w] - ref_e[:w]) / np.abs(ref_e[:w])))
+                row["energy_trace_window_steps"] = int(w)
+                row["energy_trace_tolerance"] = 1e-8
+                if "seconds" in g.files:
+                    row["reference_cpu_wall_s"] = float(g["seconds"])
+                    row["reference_cpu_threads"] = int(g["threads"]) if "threads" in g.files else None
+            out.append(row)
+            r.close()
+        except Exception as ex:  # noqa: BLE001
+            out.append({"workload": name, "error": repr(ex)})
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -385,9 +569,9 @@ def run_gpu_arm(args):
     if world != max(args.gpus, 1):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
 
-    from numericalflowiteration_b200 import measure_fp64_peak, n_quad, stride_t
+    from numericalflowiteration_b200 import measure_fp64_peak, n_quad
 
-    conf, f0, depth, desc = make_workload(args.workload, world)
+    conf, f0, depth, desc = make_workload(args.workload, world, args.scaling)
     n = args.depth or depth
     dim = conf.dim
     runner = GpuRunner(conf, f0, rank, world, torch, dist, exchange=args.exchange)
@@ -408,22 +592,19 @@ def run_gpu_arm(args):
     variant = s.last_variant
 
     # host copy of the history (for the e2e leg's upload_phi and for the CPU baseline / live parity check)
-    st_ = stride_t(conf)
-    coeffs_host = np.zeros((n + 1) * st_)
-    for lvl in range(n):
-        coeffs_host[lvl * st_:(lvl + 1) * st_] = s.download_phi(lvl)
+    coeffs_host = download_history(s, n)
+    parity = cpu = None
+    if not args.no_cpu:  # before the e2e leg: rho_full still holds what the last timed fused step consumed
+        parity, cpu = live_parity(runner, conf, f0, n, coeffs_host, args.cpu_budget, dist, world == 1)
     e2e_steps = max(3, min(args.steps, 50))
     t_e2e, h2d, d2h, _ = measure_e2e(runner, n, e2e_steps, min(args.warmup, 3), coeffs_host, torch, dist)
     e2e_value = psteps * e2e_steps / t_e2e
 
     line = None
+    peak_tf = measure_fp64_peak(local)
     if rank == 0:
-        peak_tf = measure_fp64_peak(local)
         # this rank's backtrace kernel: its share of the point-steps / its average launch duration
-        if runner.exchange == "peer-memory":  # velocity nodes rank, rank+world, ... of every spatial node
-            my_psteps = float(s.n_nodes) * len(range(rank, nq // s.n_nodes, world)) * n
-        else:
-            my_psteps = float(runner.q1 - runner.q0) * n
+        my_psteps = runner.my_point_steps(n)
         achieved_tf = my_psteps * FLOP_PER_POINT_STEP[dim] / (m["bt_ms"] * 1e-3) / 1e12
         hist_bytes = float(n) * s.stride_t * 8 + 2 * 8 * s.n_nodes
         peaks = {}
@@ -455,25 +636,13 @@ def run_gpu_arm(args):
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                     "note": "algorithmic bytes = n*stride_t*8 (history read once) + 2*8*Nnodes; shown to document the path is not HBM-bound"},
         }
-        cpu = None
-        parity = None
-        if world == 1 and not args.no_cpu:
-            run, cpu_psteps, sdesc, kind, threads, l_n, out = reference_sweep_timer(conf, f0, n, coeffs_host, args.cpu_budget)
-            run()  # warm
-            t_cpu = run()
-            cpu = {"value": cpu_psteps / t_cpu, "unit": "point-steps/s", "cores": threads, "kind": kind, "sample": sdesc,
-                   "seconds": t_cpu}
-            got = s.eval_rho(n)
-            want = out["rho"][:l_n]
-            parity = {"rho_rel_linf_vs_cpu_reference": float(np.max(np.abs(got[:l_n] - want)) / np.max(np.abs(want))),
-                      "nodes_checked": int(l_n), "tolerance": 1e-10}
         ref_cuda = None
         if world == 1 and not args.no_cpu:
             ref_cuda = reference_cuda_leg(conf, f0, n, coeffs_host, s, local, reps=3)
         line = {
             "metric": "backtrace point-steps/sec", "value": value, "unit": "point-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["t_ms"] / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "depth_n": n, "point_steps_per_step": psteps, "n_quad": nq,
                        "history": f"built on the device by {n} free-running fused steps ({t_hist:.2f} s)",
                        "l2": "flushed between timed steps (256 MiB fill, untimed; steps timed individually with CUDA events)",
@@ -488,35 +657,28 @@ def run_gpu_arm(args):
             "gpu_launches": m["launches"], "clocks": sampler.summary() if sampler else None,
             "s_per_time_step": m["t_ms"] / args.steps * 1e-3,
         }
+    runner.close()
+    del runner, s
 
-    if world == 1 and args.extras and rank == 0:
+    if args.extras:
+        # N = 1: the other dimensions / sizes.  N > 1: the 3d configurations BASELINE.json names for 2/4/8 GPUs, in STRONG form
+        # (the fixed grid, each rank 1/N of the velocity nodes) and in weak form (Nw x N), each with its own parity check.
+        plan = ([(w, "weak") for w in ("C1", "C3", "C4", "C5-16", "C5-32") if w != args.workload] if world == 1 else
+                [("C4", "strong"), ("C5-16", "strong"), ("C5-32", "strong"), ("C4", "weak"), ("C5-16", "weak"), ("C5-32", "weak")])
         extras = []
-        del runner, s
-        for name in [w for w in ("C1", "C3", "C4", "C5-16", "C5-32") if w != args.workload]:
+        for name, scaling in plan:
+            big = name == "C5-32"
             try:
-                c2, f2, d2, desc2 = make_workload(name, 1)
-                r2 = GpuRunner(c2, f2, 0, 1, torch, dist)
-                free_run(r2, d2)
-                k = 5 if c2.dim == 3 and c2.Nx >= 32 else 20
-                m2 = measure_gpu(r2, d2, k, 3, flush, torch, dist)
-                ps = float(n_quad(c2)) * d2
-                tf = ps * FLOP_PER_POINT_STEP[c2.dim] / (m2["bt_ms"] * 1e-3) / 1e12
-                ex = {"workload": desc2, "depth_n": d2, "point_steps_per_s": ps * k / (m2["t_ms"] * 1e-3),
-                      "ms_per_step": m2["t_ms"] / k, "kernel_ms": m2["bt_ms"], "variant": r2.s.last_variant,
-                      "fp64_tflops": tf, "fp64_frac": tf / line["roofline"]["peak"]}
-                if not args.no_cpu and not (c2.dim == 3 and c2.Nx >= 32):  # the reference kernel needs ~10 s per call on C5-32
-                    st2 = stride_t(c2)
-                    hist2 = np.zeros((d2 + 1) * st2)
-                    for lvl in range(d2):
-                        hist2[lvl * st2:(lvl + 1) * st2] = r2.s.download_phi(lvl)
-                    rc2 = reference_cuda_leg(c2, f2, d2, hist2, r2.s, local, reps=2)
-                    ex["reference_cuda_point_steps_per_s"] = rc2.get("value")
-                    ex["reference_cuda_kernel_ms"] = rc2.get("kernel_ms")
-                extras.append(ex)
-                r2.s.close()
+                ex = measure_workload(name, scaling, rank, world, local, args, flush, torch, dist, peak_tf, steps=5 if big else 20,
+                                      with_ref_cuda=(world == 1 or scaling == "strong"), cpu_budget=1.0)
             except Exception as e:  # noqa: BLE001
-                extras.append({"workload": name, "error": repr(e)})
-        line["other_workloads"] = extras
+                ex = {"workload": name, "scaling": scaling, "error": repr(e)}
+            if rank == 0:
+                extras.append(ex)
+        if rank == 0:
+            line["other_workloads"] = extras
+    if args.full_run and world == 1 and rank == 0:
+        line["full_run"] = full_runs(args, torch, flush)
 
     if world > 1:
         dist.barrier()
@@ -553,12 +715,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = the velocity quadrature grows with N (fixed work per GPU), strong = BASELINE's fixed grid")
     ap.add_argument("--depth", type=int, default=0, help="history depth n of the timed step (default: per workload)")
     ap.add_argument("--cpu-budget", type=float, default=3.0, help="seconds of wall time for the cpu_baseline sample")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the partial rho is exchanged (peer = stores into NVLink peer memory fused into the kernels)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", dest="extras", action="store_false")
+    ap.add_argument("--no-full-run", dest="full_run", action="store_false")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     with _StdoutToStderr():

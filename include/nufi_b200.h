@@ -152,6 +152,10 @@ int nufi_b200_interpolate(nufi_b200_handle *h, const double *values_host, double
 int nufi_b200_step(nufi_b200_handle *h, size_t n);
 /* blocking; energies[i] = electric energy of step n_begin+i, for steps run by step/solve_interpolate */
 int nufi_b200_download_energy(nufi_b200_handle *h, size_t n_begin, size_t n_end, double *energies);
+/* blocking; rho of the most recent step / peer_step / group_step / eval_rho_all as the field tail consumed it: CPU convention
+ * (1 - dV * sum f, nufi/rho.hpp:145), Nx*Ny*Nz doubles; in a multi-GPU step the SUM over all ranks' shares (identical on every
+ * GPU) -- what the reference holds in its host rho after download_rho + MPI_Allreduce (bin/test_nufi_gpu_3d.cpp:154-158) */
+int nufi_b200_download_rho_full(nufi_b200_handle *h, double *rho_host);
 /* blocking; level n (stride_t doubles, reference layout with halo) to the host */
 int nufi_b200_download_phi(nufi_b200_handle *h, size_t n, double *coeffs_level);
 int nufi_b200_sync(nufi_b200_handle *h);

@@ -25,7 +25,7 @@ SYMBOLS = [
     "nufi_b200_group_last_error", "nufi_b200_device_count", "nufi_b200_device_of",
     "nufi_b200_peer_export", "nufi_b200_peer_attach", "nufi_b200_peer_step", "nufi_b200_peer_status", "nufi_b200_peer_detach",
     "nufi_b200_group_set_exchange", "nufi_b200_group_exchange", "nufi_b200_set_kernel_timing", "nufi_b200_set_tile_nodes", "nufi_b200_eval_phase_flow",
-    "nufi_b200_set_metrics_grid_1d",
+    "nufi_b200_set_metrics_grid_1d", "nufi_b200_download_rho_full",
 ]
 
 _lib = None
@@ -70,7 +70,7 @@ def load() -> C.CDLL:
         "group_create": [C.POINTER(vp), i, C.POINTER(vp)], "group_step": [vp, sz], "group_sync": [vp],
         "group_set_exchange": [vp, i],
         "peer_export": [vp, i, vp], "peer_attach": [vp, i, i, vp], "peer_step": [vp, sz], "peer_status": [vp, C.POINTER(i)],
-        "peer_detach": [vp], "set_metrics_grid_1d": [vp, vp],
+        "peer_detach": [vp], "set_metrics_grid_1d": [vp, vp], "download_rho_full": [vp, vp],
     }.items():
         f = getattr(L, "nufi_b200_" + name)
         f.argtypes = args

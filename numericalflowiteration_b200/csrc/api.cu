@@ -377,6 +377,16 @@ int nufi_b200_eval_rho_all(nufi_b200_handle *h, size_t n, double *rho_host)
     return NUFI_B200_OK;
 }
 
+int nufi_b200_download_rho_full(nufi_b200_handle *h, double *rho_host)
+{
+    ENTER(h);
+    if (!rho_host) return fail(hh, NUFI_B200_ERR_ARG, "rho_host is NULL");
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(hh->h_pinned, hh->d_rho_full, sizeof(double) * hh->n_nodes, cudaMemcpyDeviceToHost, hh->stream));
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    std::memcpy(rho_host, hh->h_pinned, sizeof(double) * hh->n_nodes);
+    return NUFI_B200_OK;
+}
+
 int nufi_b200_solve_interpolate(nufi_b200_handle *h, size_t n, double *energy)
 {
     ENTER(h);

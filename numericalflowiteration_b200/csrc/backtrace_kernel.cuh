@@ -17,6 +17,16 @@ namespace
 
 constexpr double kMagic = 6755399441055744.0; // 1.5 * 2^52: adding it rounds to the nearest integer
 
+// s += x with the rounding error of the addition accumulated in lo (Knuth's branch-free two-sum; no fast-math: nvcc keeps the
+// order of floating-point additions)
+__device__ __forceinline__ void two_sum(double &s, double &lo, double x)
+{
+    const double t = s + x;
+    const double xv = t - s;
+    lo += (s - (t - xv)) + (x - xv);
+    s = t;
+}
+
 // Periodic cell index after a move of dk cells.  POW2: mask.  Otherwise one conditional correction each way;
 // anything further out (a point crossing more than a whole period in one step) is clamped into range and
 // flagged -- such points are recomputed by the robust slow path after the trace.
@@ -577,24 +587,29 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
     }
 
     // ---------------------------------------------------- consumer warps
-    double acc = 0;
+    // sum of f over this thread's velocities, compensated (Knuth two-sum: acc carries the rounded sum, acc_lo the rounding
+    // errors it dropped): the reference adds up to Nu*Nv*Nw terms sequentially (rho.hpp:299-306) and its result carries that
+    // sum's rounding error; here the sum is exact to an ulp whatever its length, at 6 FP64 adds per point (not per point-step)
+    double acc = 0, acc_lo = 0;
     double m0 = 0, m1 = 0, m2 = 0, m3 = 0;
     unsigned cur_tile = t_first;
     int s = 0;
     unsigned ph = 0;
 
     auto flush_tile = [&](unsigned tile) { // CTA-uniform: every consumer warp calls it
-        sred[warp][lane] = acc;
+        sred[warp][lane] = acc + acc_lo;
         consumer_sync(W * 32);
         if (warp == 0) {
-            double sum = 0;
-            for (unsigned w = 0; w < W; ++w) sum += sred[w][lane];
+            double sum = 0, lo = 0; // the consumer warps' sums in warp order, compensated as well
+            for (unsigned w = 0; w < W; ++w) two_sum(sum, lo, sred[w][lane]);
+            sum += lo;
             // TN < 32: the 32/TN lanes that traced the same node (lane % TN) are combined by a fixed shuffle tree
             for (unsigned off = 16; off >= P.TN; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
             P.slots[(static_cast<size_t>(blockIdx.x) * P.Tmax + (tile - t_first)) * 32 + lane] = static_cast<unsigned>(lane) < P.TN ? sum : 0.0;
         }
         consumer_sync(W * 32);
         acc = 0;
+        acc_lo = 0;
     };
 
     for (unsigned r = 0; r < my_rounds; ++r) {
@@ -741,7 +756,7 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
                 f = f0_3d(P, x, y, z, pt[i].vel[0], pt[i].vel[1], pt[i].vel[2]);
             }
             if (ok[i]) {
-                acc += f;
+                two_sum(acc, acc_lo, f);
                 if (P.metrics) { // nufi/cuda_kernel.cu:72-78, 264-270, 459-465
                     double vsq = v0[i][0] * v0[i][0];
                     if constexpr (DIM >= 2) vsq += v0[i][1] * v0[i][1];

@@ -141,6 +141,12 @@ class CudaScheduler:
         """Backtrace + reduce + Poisson + interpolate + store level n, asynchronously, no host round trip."""
         self._ck(self._L.nufi_b200_step(self._h, n))
 
+    def download_rho_full(self) -> np.ndarray:
+        """rho of the most recent (peer/group) step as the field tail consumed it: CPU convention, summed over all ranks."""
+        rho = np.empty(self.n_nodes)
+        self._ck(self._L.nufi_b200_download_rho_full(self._h, _ptr(rho)))
+        return rho
+
     def download_energy(self, n_begin: int, n_end: int) -> np.ndarray:
         out = np.zeros(max(n_end - n_begin, 0))
         self._ck(self._L.nufi_b200_download_energy(self._h, n_begin, n_end, _ptr(out)))

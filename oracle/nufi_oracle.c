@@ -26,6 +26,17 @@ int orc_num_threads(void)
 #endif
 }
 
+/* OpenMP thread count of the sweeps below: torchrun exports OMP_NUM_THREADS=1 to every rank, so the CPU-baseline legs of
+ * bench.py set the count explicitly (to the host's core count) instead of inheriting it. */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 static double inv_factorial(int n) /* splines.hpp:31-37 */
 {
     double f = 1.0;
@@ -488,6 +499,51 @@ void orc_rho_sweep_3d(int order, size_t n, const double *coeffs, const orc_conf3
 {
 #pragma omp parallel for schedule(dynamic, 1)
     for (size_t l = l_begin; l < l_end; ++l) rho[l] = orc_rho_3d(order, n, l, coeffs, cf, f);
+}
+
+/* ---- extended-precision sums: the same eval_ftilda values, added up in x87 long double (64-bit mantissa) instead of the
+ *      reference's running double (rho.hpp:299-306).  NOT the reference's arithmetic: a yardstick that tells whose rounding a
+ *      difference between two FP64 implementations is -- the reference's sequential sum of Nu*Nv*Nw terms carries up to
+ *      ~sqrt(Nvel) eps of relative error in dV*sum f, i.e. that divided by the perturbation amplitude in rho. ---- */
+static double rho_ext_node(int dim, int order, size_t n, size_t l, const double *coeffs, const void *cfv, const orc_f0 *f)
+{
+    long double sum = 0.0L;
+    if (dim == 1) {
+        const orc_conf1d *cf = (const orc_conf1d *)cfv;
+        const double x = cf->x_min + l * cf->dx;
+        const double du = (cf->u_max - cf->u_min) / cf->Nu, u_min = cf->u_min + 0.5 * du;
+        for (size_t ii = 0; ii < cf->Nu; ++ii) sum += (long double)orc_ftilda_1d(order, n, x, u_min + ii * du, coeffs, cf, f);
+        return (double)(1.0L - (long double)du * sum);
+    }
+    if (dim == 2) {
+        const orc_conf2d *cf = (const orc_conf2d *)cfv;
+        const size_t i = l % cf->Nx, j = l / cf->Nx;
+        const double x = cf->x_min + i * cf->dx, y = cf->y_min + j * cf->dy;
+        const double du = (cf->u_max - cf->u_min) / cf->Nu, dv = (cf->v_max - cf->v_min) / cf->Nv;
+        const double u_min = cf->u_min + 0.5 * du, v_min = cf->v_min + 0.5 * dv;
+        for (size_t jj = 0; jj < cf->Nv; ++jj)
+            for (size_t ii = 0; ii < cf->Nu; ++ii)
+                sum += (long double)orc_ftilda_2d(order, n, x, y, u_min + ii * du, v_min + jj * dv, coeffs, cf, f);
+        return (double)(1.0L - (long double)(du * dv) * sum);
+    }
+    const orc_conf3d *cf = (const orc_conf3d *)cfv;
+    const size_t k = l / (cf->Nx * cf->Ny), tmp = l % (cf->Nx * cf->Ny), j = tmp / cf->Nx, i = tmp % cf->Nx;
+    const double x = cf->x_min + i * cf->dx, y = cf->y_min + j * cf->dy, z = cf->z_min + k * cf->dz;
+    const double du = (cf->u_max - cf->u_min) / cf->Nu, dv = (cf->v_max - cf->v_min) / cf->Nv, dw = (cf->w_max - cf->w_min) / cf->Nw;
+    const double u_min = cf->u_min + 0.5 * du, v_min = cf->v_min + 0.5 * dv, w_min = cf->w_min + 0.5 * dw;
+    for (size_t kk = 0; kk < cf->Nw; ++kk)
+        for (size_t jj = 0; jj < cf->Nv; ++jj)
+            for (size_t ii = 0; ii < cf->Nu; ++ii)
+                sum += (long double)orc_ftilda_3d(order, n, x, y, z, u_min + ii * du, v_min + jj * dv, w_min + kk * dw, coeffs, cf, f);
+    return (double)(1.0L - (long double)(du * dv * dw) * sum);
+}
+
+/* dim = 1, 2, 3; cf points at the matching orc_conf{1,2,3}d */
+void orc_rho_sweep_extended(int dim, int order, size_t n, const double *coeffs, const void *cf, const orc_f0 *f, size_t l_begin,
+                            size_t l_end, double *rho)
+{
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t l = l_begin; l < l_end; ++l) rho[l] = rho_ext_node(dim, order, n, l, coeffs, cf, f);
 }
 
 /* ---- flat-q partial sums, the accumulate convention of the reference GPU path

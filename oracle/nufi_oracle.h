@@ -131,6 +131,10 @@ double orc_poisson_1d(const orc_conf1d *cf, double *data);
 double orc_poisson_2d(const orc_conf2d *cf, double *data);
 double orc_poisson_3d(const orc_conf3d *cf, double *data);
 
+/* the same sweep with the velocity sum carried in long double: a precision yardstick, not the reference's arithmetic */
+void orc_rho_sweep_extended(int dim, int order, size_t n, const double *coeffs, const void *cf, const orc_f0 *f, size_t l_begin,
+                            size_t l_end, double *rho);
+
 /* ---- fields.hpp interpolate: values at nodes -> level coefficients with (order-1) periodic halo ---- */
 void orc_interpolate_1d(int order, double *level, const double *values, const orc_conf1d *cf);
 void orc_interpolate_2d(int order, double *level, const double *values, const orc_conf2d *cf);
@@ -145,6 +149,7 @@ void orc_run_2d(int order, const orc_conf2d *cf, const orc_f0 *f, size_t n_begin
 void orc_run_3d(int order, const orc_conf3d *cf, const orc_f0 *f, size_t n_begin, size_t n_end, double *coeffs, double *energy, double *rho_out);
 
 int orc_num_threads(void);
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

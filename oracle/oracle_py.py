@@ -90,6 +90,11 @@ class Oracle:
     def threads(self) -> int:
         return int(self.lib.orc_num_threads())
 
+    def set_threads(self, n: int) -> int:
+        """OpenMP threads of the sweeps (torchrun exports OMP_NUM_THREADS=1: the CPU-baseline legs set the count explicitly)."""
+        self.lib.orc_set_num_threads(int(n))
+        return self.threads()
+
     def basis(self, order, der, x):
         out = np.zeros(order)
         self.lib.orc_bspline_basis(order, der, float(x), out)
@@ -133,6 +138,19 @@ class Oracle:
         getattr(self.lib, f"orc_rho_sweep_{conf.dim}d")(order, n, np.ascontiguousarray(coeffs), C.addressof(conf),
                                                        C.addressof(o), l_begin, l_end, out)
         return out
+
+    def rho_extended(self, conf, f0, n, coeffs, l_begin=0, l_end=None, order=4):
+        """The sweep with the velocity sum carried in long double (orc_rho_sweep_extended): tells whose rounding a difference
+        between two FP64 implementations is.  Not the reference's arithmetic."""
+        nn = _nodes(conf)
+        l_end = nn if l_end is None else l_end
+        rho = np.zeros(nn)
+        o = _f0(f0)
+        fn = self.lib.orc_rho_sweep_extended
+        fn.argtypes = [_i, _i, _sz, _dp, _p, _p, _sz, _sz, _dp]
+        fn.restype = None
+        fn(conf.dim, order, n, np.ascontiguousarray(coeffs), C.addressof(conf), C.addressof(o), l_begin, l_end, rho)
+        return rho[l_begin:l_end] if (l_begin, l_end) != (0, nn) else rho
 
     def rho_partial(self, conf, f0, n, coeffs, q_begin, q_end, rho=None, order=4):
         """GPU-convention partial: rho[l] += -dV f over flat q in [q_begin,q_end)."""
@@ -216,6 +234,10 @@ class Reference:
 
     def threads(self) -> int:
         return int(self.lib.orc_num_threads())
+
+    def set_threads(self, n: int) -> int:
+        self.lib.orc_set_num_threads(int(n))
+        return self.threads()
 
     def set_f0(self, dim, f0):
         o = _f0(f0)

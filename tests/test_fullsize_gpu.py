@@ -5,17 +5,16 @@ Gate (north_star): electric-energy trace relative error <= 1e-8 over the run.  T
 fixed relative gate is meaningful, for ANY pair of FP64 implementations (the reference's own -O2 and -O3 builds included, see
 fullsize_<case>_canonical.npz): C2 (two-stream) turns chaotic after saturation and amplifies rounding differences exponentially;
 C1 (weak Landau) damps the field energy by 13 orders of magnitude into the rounding floor.  The gate is therefore
-    |E_gpu - E_ref| / E_ref  <=  max(1e-8, 10 x spread_n, 10 x refspread_n, 2 x 1e-13 / a_n),
+    |E_gpu - E_ref| / E_ref  <=  max(1e-8, 10 x spread_n, 10 x refspread_n),
 * refspread_n = running maximum of the relative difference between the reference's own two builds (-O2 -ffp-contract=off against
   -O3 with FMA contraction; fullsize_<case>_canonical.npz, C1 and C2): 8.8e-7 by step 1000 and 5e-2 by step 1600 for C2,
   5e-8 after step 1000 for C1 -- the GPU-vs-reference differences are of the same size;
 * spread_n = running maximum of the relative difference between two GPU runs that differ ONLY in summation order (velocity
   assignment interleaved / contiguous): a deviation beyond 1e-8 is accepted only where merely reordering a sum moves the
   result by a tenth as much (C2 after step ~850: both reach 1e-2 by step 1000; until step 800 the error is < 1e-11);
-* a_n = alpha sqrt(E_n / E_0) = amplitude of the density perturbation that carries the energy E_n (E is quadratic in it, so a
-  density difference d changes E by the fraction 2 d / a_n): an energy difference equivalent to a density difference of
-  1e-13 -- a thousandth of the north star's own per-step rho tolerance of 1e-10 -- is accepted (C1 after step ~950, where
-  E_n / E_0 < 1e-9 and the trace is the rounding noise of rho = 1 - dV sum f).
+The device adds f over the velocity nodes with a compensated (two-sum) accumulation, so its rho carries an ulp of rounding where
+the reference's sequential sum carries ~sqrt(Nu) eps; what remains of |E_gpu - E_ref| late in C1 is the reference's own rounding,
+which is what refspread_n measures.
 Where the problem is well conditioned (C3, C4, the first ~850 steps of C1/C2) this is the plain 1e-8 gate; the test prints where
 it stops being one."""
 import os
@@ -29,7 +28,6 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 ENERGY_TOL = 1e-8
-RHO_EQUIV = 1e-13  # density difference whose energy equivalent is tolerated (north star: rho rel-Linf <= 1e-10 per step)
 
 
 def _fixture(name):
@@ -73,7 +71,7 @@ def test_fullsize_energy_trace(name):
     err = np.abs(got - want) / np.abs(want)
     spread = np.maximum.accumulate(np.abs(got - alt) / np.abs(want))
     a_n = f0.p[0] * np.sqrt(np.abs(want) / np.abs(want[0]))
-    tol = np.maximum(np.maximum(ENERGY_TOL, 10.0 * spread), 2.0 * RHO_EQUIV / a_n)
+    tol = np.maximum(ENERGY_TOL, 10.0 * spread)
     canon_path = os.path.join(HERE, "golden", f"fullsize_{name}_canonical.npz")
     ref_spread = None
     if os.path.exists(canon_path):  # the reference's OWN sensitivity: its -O2 -ffp-contract=off build against its -O3 FMA build
@@ -94,5 +92,6 @@ def test_fullsize_energy_trace(name):
     assert np.all(err <= tol), (int(np.argmax(err > tol)), float(err[np.argmax(err > tol)]), float(tol[np.argmax(err > tol)]))
     # last level / last rho: same rule, each against its own summation-order spread
     # (phi is linear in the density perturbation: a density difference d moves it by the fraction d / a_n; rho itself is O(1))
-    assert rel_linf(level, g["level_last"]) <= max(ENERGY_TOL, 10.0 * rel_linf(level_b, level), RHO_EQUIV / a_n[-1])
+    level_tol = max(ENERGY_TOL, 10.0 * rel_linf(level_b, level), 10.0 * float(ref_spread[-1]) if ref_spread is not None else 0.0)
+    assert rel_linf(level, g["level_last"]) <= level_tol
     assert rel_linf(rho, g["rho_last"]) <= max(1e-10, 10.0 * rel_linf(rho_b, rho))

@@ -127,7 +127,7 @@ def test_upload_download_roundtrip_and_errors(xpp, histories, monkeypatch):
         with pytest.raises(RangeError):
             s.compute_rho(0, 0, n_quad(conf) + 1)
     with pytest.raises(ValueError):
-        CudaScheduler(conf, f0, order=5)
+        CudaScheduler(conf, f0, order=9)  # orders 3..8 exist (tests/test_generic_order_gpu.py)
     with pytest.raises(ValueError):
         CudaScheduler(conf, F0(7))
 

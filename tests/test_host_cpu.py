@@ -348,8 +348,9 @@ def test_bench_reference_arm_line_contract():
     driver reads; it runs without a GPU."""
     import json
 
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2")  # what torch.distributed.run exports to rank 0
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C4", "--steps", "1",
-                        "--warmup", "3"], capture_output=True, text=True, timeout=600)
+                        "--warmup", "3", "--gpus", "2"], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -359,7 +360,13 @@ def test_bench_reference_arm_line_contract():
         assert k in d
     assert d["value"] > 0 and d["higher_is_better"] is True and d["dtype"] == "f64" and "workload" in d["config"]
     cb, e2e = d["cpu_baseline"], d["e2e"]
-    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["kind"] in ("reference", "port") and cb["value"] == d["value"] and cb["sample"]
+    assert cb["cores"] == len(os.sched_getaffinity(0))  # all host cores although the launcher exported OMP_NUM_THREADS=1
+    assert "free run of the reference CPU loop" in d["config"]["history"]  # the same problem the GPU arm free-runs, not a synthetic field
+    # the other ranks of a torchrun launch exit 0 without work and without output
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C4", "--steps", "1", "--gpus", "2"],
+                        capture_output=True, text=True, timeout=120, env=dict(env, RANK="1"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
     assert e2e["value"] == d["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
 
 
