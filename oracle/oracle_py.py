@@ -150,7 +150,7 @@ class Oracle:
         fn.argtypes = [_i, _i, _sz, _dp, _p, _p, _sz, _sz, _dp]
         fn.restype = None
         fn(conf.dim, order, n, np.ascontiguousarray(coeffs), C.addressof(conf), C.addressof(o), l_begin, l_end, rho)
-        return rho[l_begin:l_end] if (l_begin, l_end) != (0, nn) else rho
+        return rho  # full length like rho(): entries outside [l_begin, l_end) are zero
 
     def rho_partial(self, conf, f0, n, coeffs, q_begin, q_end, rho=None, order=4):
         """GPU-convention partial: rho[l] += -dV f over flat q in [q_begin,q_end)."""
@@ -402,4 +402,27 @@ def synthetic_history(conf, n_levels: int, seed: int = 1234, amp: float = 1e-2, 
         c = np.real(np.fft.ifftn(spec / sym))
         idx = [np.arange(n + order - 1) % n for n in reversed(dims)]
         out[m] = c[np.ix_(*idx)].ravel()
+    return out.ravel()
+
+
+def exact_history(conf, n_levels: int, amp: float = 1e-2, order: int = 4) -> np.ndarray:
+    """A coefficient history that every IEEE-754 machine reproduces BIT FOR BIT: only +, -, *, / on doubles (each correctly
+    rounded, no transcendental function, no FFT), so large teacher-forced inputs need not be stored -- the golden files
+    tests/golden/large_*.npz hold only the reference's rho on a few nodes of it.  Level m: periodic coefficients
+    a_m * prod_d b(frac(i_d / N_d + s_{m,d})),  b(t) = 16 t^2 (1-t)^2  (a C^1 periodic bump),  a_m and the shifts s dyadic
+    rationals from an integer hash of m; then the (order-1) halo by index wrap."""
+    dims = [conf.Nx] + ([conf.Ny] if conf.dim >= 2 else []) + ([conf.Nz] if conf.dim >= 3 else [])
+    out = np.zeros((n_levels, _stride(conf, order)))
+    for m in range(n_levels):
+        h = (m * 2654435761 + 12345) % (1 << 32)
+        a = amp * (((h >> 8) % 4096) / 2048.0 - 1.0)
+        field = np.array(a)
+        for ax, n in enumerate(reversed(dims)):  # z, y, x order: x fastest in the flattened level
+            s = ((h >> (3 * ax + 1)) % 16) / 16.0
+            t = np.arange(n) / float(n) + s
+            t = t - np.floor(t)
+            b = 16.0 * (t * t) * ((1.0 - t) * (1.0 - t))
+            field = np.multiply.outer(field, b)
+        idx = [np.arange(n + order - 1) % n for n in reversed(dims)]
+        out[m] = field[np.ix_(*idx)].ravel()
     return out.ravel()

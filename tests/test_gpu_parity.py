@@ -249,3 +249,32 @@ def test_tile_nodes_lane_layouts(name, tn, histories, oracle):
         e2 = s.download_energy(n, n + 1)[0]
         assert abs(e2 - e) <= 1e-12 * abs(e)
         assert not s.peer_timed_out()
+
+
+@pytest.mark.parametrize("name", ["C3", "C5-16", "C5-32"])
+def test_large_configurations_deep_history_against_reference_golden(name):
+    """Teacher-forced rho at BASELINE.json's full 2d2v / 3d3v sizes, deep into the history (C3: n = 100, 400, 800; C5-16, C5-32:
+    n = 25), against the REAL reference's values on nodes spread over the grid (tests/golden/large_*.npz).  The input history is
+    regenerated bit for bit from exact arithmetic (oracle_py.exact_history), so nothing large is stored."""
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from bench import make_workload
+    from oracle.oracle_py import exact_history
+
+    g = np.load(os.path.join(root, "tests", "golden", f"large_{name}.npz"))
+    conf, f0, _, desc = make_workload(name, 1)
+    assert str(g["workload"]) == desc
+    depths = [int(d) for d in g["depths"]]
+    hist = exact_history(conf, max(depths))
+    nodes = g["nodes"].astype(int)
+    with CudaScheduler(conf, f0, device=0) as s:
+        s.upload_history(hist, max(depths))
+        for n in depths:
+            got = s.eval_rho(n)[nodes]
+            want = g[f"rho_n{n}"]
+            err = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+            print(f"{name} n={n} [{s.last_variant}]: rho rel-Linf over {len(nodes)} sampled nodes {err:.2e}")
+            assert err <= RHO_TOL, (name, n, err)

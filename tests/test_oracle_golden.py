@@ -205,3 +205,31 @@ def test_generic_order_live_reference(order, oracle, reference):
         want = reference.rho_order(conf, f0, order, n_lev, coeffs)
         assert np.array_equal(oracle.rho(conf, f0, n_lev, coeffs, order=order), want), (name, order)
         assert rel_linf(oracle.interpolate(conf, want, order=order), reference.interpolate_order(conf, order, want)) <= 1e-11
+
+
+# ------------------------------------------------------------------ large configurations, deep histories (tests/golden/large_*.npz)
+def _large(name):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(HERE))
+    from bench import make_workload
+    from oracle.oracle_py import exact_history
+
+    g = np.load(os.path.join(HERE, "golden", f"large_{name}.npz"))
+    conf, f0, _, desc = make_workload(name, 1)
+    assert str(g["workload"]) == desc
+    return conf, f0, g, exact_history
+
+
+@pytest.mark.parametrize("name,depth", [("C3", 100), ("C3", 400), ("C5-16", 25), ("C5-32", 25)])
+def test_large_teacher_forced_rho_bit_exact(name, depth, oracle):
+    """BASELINE.json's 2d2v / 3d3v configurations at full size, deep into the history: the reference's rho (real reference,
+    tests/golden/make_large_golden.py) on nodes spread over the grid, input = the bit-reproducible exact_history.  (C3 at n = 800
+    is left to the GPU suite: 1e8 point-steps of the canonical single-thread-per-node oracle.)"""
+    conf, f0, g, exact_history = _large(name)
+    hist = exact_history(conf, depth)
+    import hashlib
+
+    assert np.array_equal(np.frombuffer(hashlib.sha256(hist[:64].tobytes()).digest(), dtype=np.uint8), g["history_sha256_first_level"])
+    for l, want in zip(g["nodes"], g[f"rho_n{depth}"]):
+        assert oracle.rho(conf, f0, depth, hist, int(l), int(l) + 1)[int(l)] == want, (name, depth, int(l))

@@ -29,8 +29,8 @@ def test_c5_rho_against_the_extended_precision_sum(nx, oracle):
         hist = np.concatenate([s.download_phi(m) for m in range(n)] + [np.zeros(st)])
         variant = s.last_variant
     l_n = nx  # one x-row of nodes: nx * nx^3 * n point-steps on the CPU, twice
-    ext = oracle.rho_extended(conf, f0, n, hist, 0, l_n)
-    ref = oracle.rho(conf, f0, n, hist, 0, l_n)
+    ext = oracle.rho_extended(conf, f0, n, hist, 0, l_n)[:l_n]
+    ref = oracle.rho(conf, f0, n, hist, 0, l_n)[:l_n]
     scale = float(np.max(np.abs(ext)))
     err_gpu = float(np.max(np.abs(rho[:l_n] - ext))) / scale
     err_ref = float(np.max(np.abs(ref - ext))) / scale

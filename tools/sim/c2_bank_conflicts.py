@@ -4,7 +4,7 @@
 Traces every quadrature point of C2 (256 x 512) back through the n = 800 levels of the reference CPU loop's history (numpy,
 vectorised) and counts the LDS.64 wavefronts of the kernel's lane layout: a warp = 32 x-neighbouring nodes sharing one velocity;
 a 64-bit shared-memory load is served per half-warp; two lanes of a half-warp conflict iff their cells differ but are congruent
-mod 16 (level format: 3 doubles per cell -> bank pair (3 c + j) mod 16).  Then evaluates lane re-packing strategies.
+mod 16 (level format: 3 doubles per cell -> bank pair (3 c + j) mod 16).  Then evaluates what wider loads would change.
 
     python tools/sim/c2_bank_conflicts.py [history.npy]
 """
@@ -57,38 +57,17 @@ def halfwarp_degree(c):
     return deg
 
 
-def repack(c):
-    """c: [..., 32] cells of a warp.  Returns a permutation (slot -> lane) that puts, for every residue class mod 16, the first
-    distinct... simple model: lanes ranked within their residue class (distinct cells only; duplicates of a cell ride along);
-    rank 0 -> half-warp 0, rank 1 -> half-warp 1, others fill the free slots."""
-    shp = c.shape[:-1]
-    c2 = c.reshape(-1, 32)
-    out = np.empty_like(c2)
-    for w in range(c2.shape[0]):
-        cw = c2[w]
-        halves = [[], []]
-        left = []
-        seen = {}
-        for lane in range(32):
-            r = cw[lane] & 15
-            key = (r, cw[lane])
-            if key in seen:  # same cell as an earlier lane: broadcast, goes wherever that one went if room
-                h = seen[key]
-                if len(halves[h]) < 16:
-                    halves[h].append(lane)
-                    continue
-            used = [k for k in seen if k[0] == r]
-            rank = len(set(used))
-            if rank < 2 and len(halves[rank]) < 16:
-                halves[rank].append(lane)
-                seen[key] = rank
-            else:
-                left.append(lane)
-        for lane in left:
-            h = 0 if len(halves[0]) < 16 else 1
-            halves[h].append(lane)
-        out[w] = cw[np.array(halves[0] + halves[1])]
-    return out.reshape(*shp, 32)
+def group_degree(c, lanes):
+    """c: [..., lanes] cells of one wavefront group (16 lanes for a 64-bit load, 8 for a 128-bit load whose lane stride is 16 B):
+    max number of DISTINCT cells per residue class mod `lanes` = wavefronts that group's load takes."""
+    c = np.sort(c, axis=-1)
+    res = c % lanes
+    first = np.ones(c.shape, dtype=bool)
+    first[..., 1:] = c[..., 1:] != c[..., :-1]
+    deg = np.zeros(c.shape[:-1], dtype=np.int64)
+    for r in range(lanes):
+        deg = np.maximum(deg, np.sum(first & (res == r), axis=-1))
+    return deg
 
 
 def main():
@@ -106,39 +85,15 @@ def main():
     print("per-velocity ratio (every 32nd):", np.round(per_vel[::32], 2))
     by_age = deg.mean(axis=(1, 2, 3))
     print("by history age (newest first, every 100 levels):", np.round(by_age[::100], 2))
-    # re-pack every K levels, keep the permutation for the next K levels
-    sub = tiles[:, :, ::8, :]  # every 8th velocity to keep the python loop affordable
-    for K in (1, 4, 16, 64):
-        tot = 0
-        cnt = 0
-        for l0 in range(0, L, K):
-            blk = sub[l0:l0 + K]
-            perm_src = repack(blk[0])  # cells after re-pack at the first level of the block
-            # derive the permutation indices: recompute on lane ids
-            ids = np.broadcast_to(np.arange(32), blk[0].shape)
-            # permutation by matching: redo repack on (cell*64+lane) trick
-            keyed = blk[0].astype(np.int64) * 64 + ids
-            order = np.empty_like(keyed)
-            flat_c = blk[0].reshape(-1, 32)
-            flat_o = order.reshape(-1, 32)
-            rp = repack(blk[0]).reshape(-1, 32)
-            for w in range(flat_c.shape[0]):
-                # map re-packed cells back to lanes (stable for duplicates)
-                lanes = list(range(32))
-                res = []
-                for cval in rp[w]:
-                    for j, ln in enumerate(lanes):
-                        if flat_c[w, ln] == cval:
-                            res.append(ln)
-                            lanes.pop(j)
-                            break
-                flat_o[w] = res
-            perm = order  # [tile, vel, 32] slot -> lane
-            for l in range(blk.shape[0]):
-                c = np.take_along_axis(blk[l], perm, axis=-1)
-                tot += halfwarp_degree(c.reshape(*c.shape[:-1], 2, 16)).sum()
-                cnt += c.size // 16
-        print(f"re-pack every {K:3d} levels: wavefront ratio {tot / cnt:.3f}")
+    # what wider loads would buy: a 128-bit load is served per quarter-warp (8 lanes), so it takes a stretch of 1/7 instead of 1/15
+    q = group_degree(tiles.reshape(L, Nx // 32, Nu, 4, 8), 8)
+    r128 = q.sum() / q.size
+    print(f"128-bit loads (8-lane groups): wavefront ratio {r128:.3f}")
+    now = 3 * 2 * base / ideal
+    print(f"wavefronts per warp-step: now (3 x LDS.64) {now:.2f};  (p0,p1) as one LDS.128 + p2 as LDS.64: {4 * r128 + 2 * base / ideal:.2f};"
+          f"  two LDS.128 (padded cell): {8 * r128:.2f};  conflict-free floor 6")
+    span = tiles.max(axis=-1).astype(np.int64) - tiles.min(axis=-1)
+    print("warp span in cells (32 lanes, 31 = rigid): percentiles 50/90/99:", np.percentile(span, [50, 90, 99]))
 
 
 if __name__ == "__main__":
