@@ -61,49 +61,17 @@ __global__ void __launch_bounds__(256) finish_rho_kernel(const __grid_constant__
     }
 }
 
-// finish_rho_kernel fused with the peer exchange (multi-GPU step): the tile's rho values are stored straight into the
-// exchange buffer of EVERY GPU (own one included; remote stores travel over NVLink), and the last block to finish releases
-// this rank's flag on every GPU.  grid = max(n_tiles, 1) blocks: a rank without work only raises its flags.
-__global__ void __launch_bounds__(256) finish_push_kernel(const __grid_constant__ FinishParams F, const __grid_constant__ PeerPush X)
+// A rank without work in a multi-GPU step (more ranks than velocity nodes) still owes every GPU its counter units and an
+// (empty) header for this epoch.
+__global__ void peer_noop_kernel(const __grid_constant__ PeerPush X)
 {
-    __shared__ double part[8][32];
     pdl_wait();
     pdl_trigger();
-    const unsigned tile = blockIdx.x;
-    const int lane = threadIdx.x & 31;
-    const unsigned wj = threadIdx.x >> 5;
-    if (tile < F.n_tiles) {
-        const unsigned b_lo = (tile * F.rpt) / F.rpc;
-        const unsigned b_hi = ((tile + 1) * F.rpt - 1) / F.rpc;
-        double sum = 0;
-        for (unsigned b = b_lo + wj; b <= b_hi; b += 8) {
-            const unsigned t_first = (b * F.rpc) / F.rpt;
-            sum += F.slots[(static_cast<size_t>(b) * F.Tmax + (tile - t_first)) * 32 + lane];
-        }
-        part[wj][lane] = sum;
-        __syncthreads();
-        if (wj == 0) {
-            double tot = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) tot += part[w][lane];
-            const unsigned long long l = F.l_first + static_cast<unsigned long long>(tile) * F.TN + lane;
-            if (static_cast<unsigned>(lane) < F.TN && l <= F.l_last) {
-                const double val = -F.dV * tot;
-                F.rho_partial[l] = val;
-                if (F.rho_full) F.rho_full[l] = 1 - F.dV * tot;
-                for (int p = 0; p < X.world; ++p) X.data[p][l] = val;
-            }
-        }
-    }
-    __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system(); // cumulative: this block's remote stores (observed through the barrier) before its ticket
-        const unsigned t = atomicAdd(X.ticket, 1u);
-        if (t == gridDim.x - 1) { // every block has stored and fenced
-            *X.ticket = 0;
-            __threadfence_system();
-            for (int p = 0; p < X.world; ++p) st_relaxed_sys(X.flag[p], X.epoch);
-        }
+        for (int p = 0; p < X.world; ++p) *X.header[p] = X.hdr;
+        __threadfence_system();
+        for (int p = 0; p < X.world; ++p)
+            asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(X.counter[p]), "l"(kPeerUnit) : "memory");
     }
 }
 
@@ -382,7 +350,12 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     const size_t smem_bytes = kSmemFixed + (staged ? static_cast<size_t>(P.stages) * P.stage_bytes : 0);
 
     // ---- slots: one per (CTA, tile it touches); every slot the finish kernel reads is written by its CTA
-    if (!metrics) {
+    const bool push = !metrics && h->peer_push; // multi-GPU step: the slots live in the exchange buffers of all GPUs
+    if (push) {
+        const size_t need = static_cast<size_t>(grid) * P.Tmax * 32;
+        if (need > h->px.slot_cap)
+            return fail(h, NUFI_B200_ERR_ARG, "peer step: this launch shape needs more slot space than the exchange buffer holds (nodes per tile forced below 32?)");
+    } else if (!metrics) {
         const size_t need = static_cast<size_t>(grid) * P.Tmax * 32;
         if (need > h->partials_cap) {
             if (h->d_partials) cudaFree(h->d_partials);
@@ -401,7 +374,17 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     // ---- slot reduction: by the fused tail (defer), else by the kernel's own last-CTA epilogue (optionally pushing to the peers)
     EpilogueParams E{};
     bool tail_reduces = false;
-    if (!metrics) {
+    if (push) {
+        E.mode = 3;
+        E.n_active = (P.R + P.rpc - 1) / P.rpc;
+        E.X = h->px.push;
+        PeerHeader &H = E.X.hdr;
+        H.rpt = P.rpt; H.rpc = P.rpc; H.Tmax = P.Tmax; H.n_tiles = P.n_tiles; H.TN = P.TN; H.n_ctas = E.n_active;
+        H.dV = h->dim == 1 ? P.du : (h->dim == 2 ? P.du * P.dv : P.du * P.dv * P.dw); // rho.hpp:145, 307, 459
+        H.l_first = P.l_first; H.l_last = P.l_last;
+        h->px.push.hdr = H; // the tail tabulates its slot loads from this rank's geometry before the peers' headers arrive
+        h->fin_pending = false;
+    } else if (!metrics) {
         FinishParams F{};
         F.slots = h->d_partials;
         F.rho_partial = h->d_rho_partial;
@@ -415,20 +398,18 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
         F.TN = P.TN;
         if (!all_nodes) NUFI_CUDA_CHECK(h, cudaMemsetAsync(h->d_rho_partial, 0, sizeof(double) * h->n_nodes, h->stream));
         h->fin = F;
-        tail_reduces = defer_finish && whole && !h->fin_push;
+        tail_reduces = defer_finish && whole;
         h->fin_pending = tail_reduces;
         // many tiles (TN < 32 on a large grid): the one-CTA epilogue would serialise them; use the multi-block finish kernels
         const bool epilogue = P.n_tiles <= 256;
         if (!tail_reduces && !epilogue) {
-            h->fin_pending = true; // launch_finish() below runs finish_rho_kernel / finish_push_kernel (h->fin_push kept)
+            h->fin_pending = true; // launch_finish() below runs finish_rho_kernel
         } else if (!tail_reduces) {
-            E.mode = h->fin_push ? 2 : 1;
+            E.mode = 1;
             E.n_active = (P.R + P.rpc - 1) / P.rpc;
             E.done = h->d_done;
             E.F = F;
-            if (h->fin_push) E.X = h->px.push;
         }
-        if (tail_reduces || epilogue) h->fin_push = false;
     }
 
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -525,22 +506,19 @@ int launch_sample_field(Handle *h, const double *d_ref_level, int der, size_t np
     return NUFI_B200_OK;
 }
 
-int launch_flag_only_push(Handle *h)
+int launch_peer_noop(Handle *h)
 {
-    FinishParams F{};
-    F.n_tiles = 0;
-    h->fin = F;
-    h->fin_pending = true;
-    h->fin_push = true;
-    return launch_finish(h);
+    h->px.push.hdr = PeerHeader{}; // n_tiles = 0: nothing to add for this rank
+    PeerPush X = h->px.push;
+    NUFI_CUDA_CHECK(h, launch_chained(h, peer_noop_kernel, dim3(1), dim3(32), 0, X));
+    h->launches += 1;
+    return NUFI_B200_OK;
 }
 
 int launch_finish(Handle *h)
 {
     if (!h->fin_pending) return NUFI_B200_OK;
-    if (h->fin_push) NUFI_CUDA_CHECK(h, launch_chained(h, finish_push_kernel, dim3(h->fin.n_tiles ? h->fin.n_tiles : 1), dim3(256), 0, h->fin, h->px.push));
-    else NUFI_CUDA_CHECK(h, launch_chained(h, finish_rho_kernel, dim3(h->fin.n_tiles), dim3(256), 0, h->fin));
-    h->fin_push = false;
+    NUFI_CUDA_CHECK(h, launch_chained(h, finish_rho_kernel, dim3(h->fin.n_tiles), dim3(256), 0, h->fin));
     NUFI_CUDA_CHECK(h, cudaGetLastError());
     h->fin_pending = false;
     h->launches += 1;

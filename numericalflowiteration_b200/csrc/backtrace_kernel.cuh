@@ -492,13 +492,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 // named barrier over the consumer warps only (the producer warp never joins)
 __device__ __forceinline__ void consumer_sync(unsigned threads) { asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); }
 
-// peer-memory primitive: the exchange flags are raised with fence.sys + relaxed system-scope store, read with ld.acquire.sys;
-// after a fence.sys by the same thread a relaxed system-scope store completes the release pattern (PTX memory model)
-__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
 constexpr int kMaxStages = 8;
 constexpr unsigned kBarBytes = 2 * kMaxStages * 8; // full[8], empty[8]
 constexpr unsigned kRedBytes = 32 * 32 * 8;        // consumer-warp reduction scratch [32 warps][32 lanes]
@@ -527,7 +520,7 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
     __shared__ unsigned int s_ticket;
     __shared__ unsigned short s_tfirst[256]; // epilogue: first tile of every CTA (filled below, read by the last CTA only)
     pdl_trigger(); // the slot reduction / field tail behind this launch may be scheduled as soon as an SM has room
-    if (E.mode) // visible to the epilogue through the CTA's barriers (the producer warp's share through the __syncthreads below)
+    if (E.mode == 1) // visible to the epilogue through the CTA's barriers (the producer warp's share through the __syncthreads below)
         for (unsigned b = threadIdx.x; b < E.n_active && b < 256; b += blockDim.x)
             s_tfirst[b] = static_cast<unsigned short>((b * E.F.rpc) / E.F.rpt);
     extern __shared__ __align__(128) unsigned char smem[];
@@ -605,7 +598,13 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
             sum += lo;
             // TN < 32: the 32/TN lanes that traced the same node (lane % TN) are combined by a fixed shuffle tree
             for (unsigned off = 16; off >= P.TN; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
-            P.slots[(static_cast<size_t>(blockIdx.x) * P.Tmax + (tile - t_first)) * 32 + lane] = static_cast<unsigned>(lane) < P.TN ? sum : 0.0;
+            const size_t slot = (static_cast<size_t>(blockIdx.x) * P.Tmax + (tile - t_first)) * 32 + lane;
+            const double val = static_cast<unsigned>(lane) < P.TN ? sum : 0.0;
+            if (E.mode == 3) { // multi-GPU step: the slot goes straight into every GPU's exchange buffer (NVLink stores; own GPU included)
+                for (int p = 0; p < E.X.world; ++p) E.X.slots[p][slot] = val;
+            } else {
+                P.slots[slot] = val;
+            }
         }
         consumer_sync(W * 32);
         acc = 0;
@@ -772,7 +771,28 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
 
     if (!P.metrics) {
         flush_tile(cur_tile);
-        if (E.mode) { // ---- epilogue: the last CTA to arrive reduces the slots of all tiles (and pushes them to the peers)
+        if (E.mode == 3) { // ---- multi-GPU step: this CTA's slots are on their way to every GPU; sign off on the peers' counters
+            // (flush_tile ended with a barrier over the consumer warps: thread 0 has observed every remote slot store of this CTA, so
+            //  its one cumulative system-scope fence orders them all before the counter updates -- the release side of the tail's
+            //  ld.acquire.sys.)  CTA 0 also publishes the launch geometry and tops the count up to kPeerUnit per rank and epoch.
+            if (threadIdx.x == 0) {
+#ifdef NUFI_TAIL_TIMING
+                const long long tk0 = clock64();
+#endif
+                if (blockIdx.x == 0)
+                    for (int p = 0; p < E.X.world; ++p) *E.X.header[p] = E.X.hdr;
+                __threadfence_system();
+#ifdef NUFI_TAIL_TIMING
+                const long long tk1 = clock64();
+#endif
+                const unsigned long long inc = blockIdx.x == 0 ? kPeerUnit - (E.n_active - 1) : 1ull;
+                for (int p = 0; p < E.X.world; ++p)
+                    asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(E.X.counter[p]), "l"(inc) : "memory");
+#ifdef NUFI_TAIL_TIMING
+                if (blockIdx.x == 0 || blockIdx.x == 77) printf("push sign-off CTA %u (cycles): fence.sys %lld  counter adds %lld\n", blockIdx.x, tk1 - tk0, clock64() - tk1);
+#endif
+            }
+        } else if (E.mode) { // ---- epilogue: the last CTA to arrive reduces the slots of all tiles
             // (flush_tile ended with a barrier over the consumer warps: thread 0 has observed every slot store of this CTA, so its
             //  one cumulative fence orders them all before the ticket -- the pattern of cooperative-groups grid sync.  A fence in
             //  every thread costs microseconds here, and tens of them at system scope below.)
@@ -819,20 +839,11 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
                         for (int w = 0; w < 8; ++w) tot += sred[8 * k + w][lane];
                         const unsigned long long l = F.l_first + static_cast<unsigned long long>(tile) * F.TN + lane;
                         if (static_cast<unsigned>(lane) < F.TN && l <= F.l_last) {
-                            const double val = -F.dV * tot;
-                            F.rho_partial[l] = val;
+                            F.rho_partial[l] = -F.dV * tot;
                             if (F.rho_full) F.rho_full[l] = 1 - F.dV * tot;
-                            if (E.mode == 2)
-                                for (int p = 0; p < E.X.world; ++p) E.X.data[p][l] = val; // NVLink stores into every GPU's buffer
                         }
                     }
                     consumer_sync(W * 32);
-                }
-                if (E.mode == 2) { // the batch loop ended with a barrier: lanes 0..world-1 of warp 0 have observed all remote stores
-                    if (warp == 0) {
-                        __threadfence_system(); // ONE system-scope fence (warp 0), then the flags go out to all peers in parallel
-                        if (lane < E.X.world) st_relaxed_sys(E.X.flag[lane], E.X.epoch);
-                    }
                 }
                 if (threadIdx.x == 0) *E.done = 0; // every participant has arrived: ready for the next launch
             }

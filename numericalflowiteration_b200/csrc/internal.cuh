@@ -82,33 +82,50 @@ struct FinishParams
 };
 
 // ----------------------------------------------------------------------------------------------
-// Peer exchange of the partial rho over NVLink/NVSwitch peer memory (peer.cu).  Every GPU owns an exchange buffer
-//   [flags: 2 parities x kMaxPeers x u64][data: 2 parities x world x n_nodes doubles]
+// Peer exchange of the partial rho over NVLink/NVSwitch peer memory (peer.cu).  What travels are the backtrace kernel's own
+// per-(CTA, tile) SLOTS: every GPU owns an exchange buffer
+//   [counters: 2 parities x kMaxPeers x u64][headers: 2 x kMaxPeers x PeerHeader][slots: 2 x world x slot_cap doubles]
 // mapped into all peers (one process: cudaDeviceEnablePeerAccess; one process per GPU: CUDA IPC).  Per step with epoch e
-// (parity e&1) rank r STORES its partial rho straight into data[e&1][r] of every GPU, then releases flag[e&1][r] = e
-// there; the field tail of every GPU acquires the world flags and adds the contributions in rank order.
+// (parity e&1) every CTA of rank r STORES each slot it finishes straight into region [e&1][r] of EVERY GPU (its own included),
+// and when it is done fences once and adds to counter[e&1][r] on every GPU; CTA 0 also writes the launch geometry (header) and
+// tops the counter up so that every rank contributes exactly kPeerUnit per epoch whatever its CTA count.  No last-CTA
+// reduction, no serial epilogue: the kernel ends when its CTAs end.  The field tail of every GPU acquires the world counters
+// and adds all ranks' slots in a fixed order (bit-identical on every GPU).
 // ----------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 16;
-constexpr size_t kPeerFlagBytes = 2 * kMaxPeers * sizeof(unsigned long long);
+constexpr unsigned long long kPeerUnit = 1ull << 20; // counter units one rank contributes per epoch (> any CTA count)
 
-struct PeerPush // sender side (finish_push_kernel)
+struct PeerHeader // launch geometry of one rank's backtrace kernel: where its slots are and how to add them (64 bytes)
 {
-    double *data[kMaxPeers];            // data[e&1][my rank] inside every GPU's exchange buffer
-    unsigned long long *flag[kMaxPeers]; // flag[e&1][my rank] inside every GPU's exchange buffer
+    unsigned int rpt, rpc, Tmax, n_tiles, TN, n_ctas;
+    double dV;
+    unsigned long long l_first, l_last;
+    unsigned long long pad[2];
+};
+static_assert(sizeof(PeerHeader) == 64, "PeerHeader is 64 bytes");
+
+constexpr size_t kPeerCounterBytes = 2 * kMaxPeers * sizeof(unsigned long long);
+constexpr size_t kPeerHeaderBytes = 2 * kMaxPeers * sizeof(PeerHeader);
+
+struct PeerPush // sender side (backtrace kernel, epilogue mode 3)
+{
+    double *slots[kMaxPeers];               // region [e&1][my rank] inside every GPU's exchange buffer
+    unsigned long long *counter[kMaxPeers]; // counter[e&1][my rank] inside every GPU's exchange buffer
+    PeerHeader *header[kMaxPeers];          // header[e&1][my rank] inside every GPU's exchange buffer
     int world;
-    unsigned long long epoch;
-    unsigned int *ticket;               // local last-block counter
+    PeerHeader hdr;                         // this launch's geometry (written by CTA 0)
 };
 
 struct PeerRecv // receiver side (tail_small_kernel / peer_gather_kernel)
 {
-    int world;                          // 0: not a peer step
-    const unsigned long long *flags;    // local flag[e&1][0..world)
-    const double *data;                 // local data[e&1][0..world)[n_nodes]
-    unsigned long long epoch;
-    unsigned long long l_first[kMaxPeers], l_last[kMaxPeers]; // node range each rank contributes to (first > last: none)
-    double *rho_full;                   // CPU-convention rho (1 + sum) for later downloads
-    int *status;                        // set to 1 if a flag never arrived (bounded spin)
+    int world;                              // 0: not a peer step
+    const unsigned long long *counters;     // local counter[e&1][0..world)
+    unsigned long long target;              // value every counter reaches once its rank's epoch-e pushes have all landed
+    const PeerHeader *headers;              // local header[e&1][0..world)
+    const double *slots;                    // local region [e&1][0]; rank r at + r * slot_cap
+    size_t slot_cap;                        // doubles per (parity, rank) region
+    double *rho_full;                       // CPU-convention rho (1 - dV * sum) for later downloads
+    int *status;                            // set to 1 if a counter never arrived (bounded spin)
 };
 
 #ifdef __CUDACC__
@@ -119,18 +136,19 @@ struct PeerRecv // receiver side (tail_small_kernel / peer_gather_kernel)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// Receiver: thread r < world spins (bounded, ~17 s; not at all once a wait has already given up) until rank r's flag of this epoch has arrived.  Call from all threads
-// of the block and follow with __syncthreads(); read the data with __ldcg (L2: the peers wrote it behind L1's back).
+// Receiver: thread r < world spins (bounded, ~17 s; not at all once a wait has already given up) until rank r's counter of this
+// parity has reached the epoch's target.  Call from all threads of the block and follow with __syncthreads(); read the slots
+// with __ldcg (L2: the peers wrote them behind L1's back).
 __device__ __forceinline__ void peer_wait_all(const PeerRecv &X)
 {
     if (static_cast<int>(threadIdx.x) < X.world) {
-        const unsigned long long *f = X.flags + threadIdx.x;
+        const unsigned long long *f = X.counters + threadIdx.x;
         const long long t0 = clock64();
         const bool gave_up_before = *reinterpret_cast<volatile int *>(X.status) != 0; // sticky: later steps do not wait again
         for (;;) {
             unsigned long long v;
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-            if (v >= X.epoch || gave_up_before) break;
+            if (v >= X.target || gave_up_before) break;
             if (clock64() - t0 > (1ll << 35)) { // a peer never pushed: do not hang the GPU, report through the status word
                 *X.status = 1;
                 break;
@@ -139,13 +157,42 @@ __device__ __forceinline__ void peer_wait_all(const PeerRecv &X)
     }
 }
 
-// rho[l] = 1 + sum over the ranks that cover node l, in rank order (identical on every GPU)
-__device__ __forceinline__ double peer_sum(const PeerRecv &X, size_t n_nodes, unsigned long long l)
+// One of the 8 strided partial sums of a node over the slots of ALL ranks: for w in 0..7, the slots of CTAs b_lo+w, b_lo+w+8, ...
+// of rank 0, then of rank 1, ... (loads four at a time; + 0.0 is exact, so the order is that of one-by-one addition).
+__device__ __forceinline__ double peer_slot_sum(const PeerRecv &X, unsigned long long l, int w)
 {
     double sum = 0;
-    for (int r = 0; r < X.world; ++r)
-        if (l >= X.l_first[r] && l <= X.l_last[r]) sum += __ldcg(X.data + static_cast<size_t>(r) * n_nodes + l);
-    return 1 + sum;
+    for (int r = 0; r < X.world; ++r) {
+        const PeerHeader H = X.headers[r];
+        if (H.n_tiles == 0 || l < H.l_first || l > H.l_last) continue;
+        const unsigned long long rel = l - H.l_first;
+        const unsigned tile = static_cast<unsigned>(rel / H.TN), lane = static_cast<unsigned>(rel % H.TN);
+        const unsigned b_lo = (tile * H.rpt) / H.rpc, b_hi = ((tile + 1) * H.rpt - 1) / H.rpc;
+        const double *slots = X.slots + static_cast<size_t>(r) * X.slot_cap;
+        for (unsigned b = b_lo + w; b <= b_hi; b += 32) {
+            double v[4];
+#pragma unroll
+            for (unsigned u = 0; u < 4; ++u) {
+                const unsigned bb = b + 8 * u;
+                v[u] = 0.0;
+                if (bb <= b_hi) {
+                    const unsigned t_first = (bb * H.rpc) / H.rpt;
+                    v[u] = __ldcg(slots + (static_cast<size_t>(bb) * H.Tmax + (tile - t_first)) * 32 + lane);
+                }
+            }
+            sum = (((sum + v[0]) + v[1]) + v[2]) + v[3];
+        }
+    }
+    return sum;
+}
+
+// rho[l] = 1 - dV * (sum of the 8 partial sums, in order): identical on every GPU
+__device__ __forceinline__ double peer_rho(const PeerRecv &X, unsigned long long l)
+{
+    double tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += peer_slot_sum(X, l, w);
+    return 1 - X.headers[0].dV * tot;
 }
 #endif
 
@@ -157,18 +204,19 @@ struct PeerState
     size_t xb_bytes = 0;
     unsigned char *peer_xb[kMaxPeers] = {};
     unsigned long long epoch = 0;
-    unsigned int *d_ticket = nullptr;
+    size_t slot_cap = 0;                // doubles per (parity, rank) slot region
     int *d_status = nullptr;
     PeerPush push{};                    // of the step being launched
     PeerRecv recv{};
 };
 
-// In-kernel epilogue of the backtrace kernel (rho mode): the last CTA to finish adds the slots of every tile in a fixed order
-// (what finish_rho_kernel does as a separate launch) and, in a multi-GPU step, stores the result into every GPU's exchange
-// buffer and releases this rank's flags there (finish_push_kernel).  mode 0: none -- the fused tail reduces the slots itself.
+// In-kernel epilogue of the backtrace kernel (rho mode).  mode 1: the last CTA to finish adds the slots of every tile in a fixed
+// order (what finish_rho_kernel does as a separate launch).  mode 3 (multi-GPU step): no reduction here at all -- every CTA has
+// stored its slots into every GPU's exchange buffer as it went and only signs off on the peers' counters (PeerPush).  mode 0:
+// none -- the fused tail reduces the slots itself.
 struct EpilogueParams
 {
-    int mode;                 // 0 none, 1 finish, 2 finish + push to the peers
+    int mode;                 // 0 none, 1 finish (last-CTA slot reduction), 3 push every slot to the peers (multi-GPU step)
     unsigned int n_active;    // CTAs that take part (blockIdx.x < n_active)
     unsigned int *done;       // device counter, zero between launches
     FinishParams F;
@@ -227,7 +275,7 @@ struct Handle
     unsigned int *d_done = nullptr; // arrival counter of the backtrace kernel's last-CTA epilogue
     unsigned long long vstride = 1, voff = 0; // velocity share of the next backtrace launch (multi-GPU step), else 1, 0
     PeerState px;
-    bool fin_push = false;       // the pending slot reduction also pushes to the peers (finish_push_kernel)
+    bool peer_push = false;      // the next backtrace launch pushes its slots into every GPU's exchange buffer (peer_step)
     int tn_force = 0;            // nodes per tile forced by nufi_b200_set_tile_nodes (0: automatic)
     bool mgrid_set = false;      // 1d: compute_metrics integrates over `mconf`'s (x,u) grid instead of the field grid's
     nufi_b200_config1d mconf{};
@@ -295,7 +343,7 @@ void peer_free(Handle *h);
 int peer_alloc(Handle *h, int world);
 int peer_prepare_step(Handle *h);                 // next epoch: fills h->px.push / h->px.recv
 int launch_peer_gather(Handle *h);                // exchange buffer -> d_rho_full (large grids, cuFFT tail)
-int launch_flag_only_push(Handle *h);             // a rank with an empty q-range still has to raise its flags
+int launch_peer_noop(Handle *h);                  // a rank without work still has to contribute its counter units
 int tail_filter(Handle *h, const double *d_values, int mode); // 1: poisson solve, 2: interpolate; result in d_field
 int expand_field_to_stage(Handle *h);
 double *tail_energy_scratch(Handle *h);

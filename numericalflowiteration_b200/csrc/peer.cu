@@ -3,12 +3,14 @@
 // Replaces the reference's fan-in (cuda_kernel::download_rho's blocking copy + host add per device, nufi/cuda_kernel.cu:135-145,
 // nufi/cuda_scheduler.hpp:113-118, and MPI_Allreduce on host buffers, bin/test_nufi_gpu_3d.cpp:158) -- and the NCCL all-reduce
 // this library used first -- by direct stores into peer memory:
-//   * finish_push_kernel (backtrace.cu): the slot reduction that produces this GPU's partial rho writes it into the exchange
-//     buffer of EVERY GPU (NVLink stores) and the last block releases a per-(rank, parity) epoch flag on every GPU;
-//   * the field tail (tail_small_kernel / peer_gather_kernel) acquires the `world` flags and adds the contributions in rank
-//     order, so all replicas compute bit-identical rho, phi and histories with no collective call, no extra launch for the
-//     reduction and no host synchronisation.  Two parities make the buffers safe to reuse: a rank can only write epoch e+2
+//   * the backtrace kernel (epilogue mode 3, backtrace_kernel.cuh): every CTA stores each per-(CTA, tile) slot it finishes into
+//     the exchange buffer of EVERY GPU (NVLink stores) and, when it is done, fences once and adds to a per-(rank, parity) counter
+//     on every GPU.  There is no reduction and no serial section in the kernel: it ends when its CTAs end;
+//   * the field tail (tail_small_kernel / peer_gather_kernel) acquires the `world` counters and adds the slots of all ranks in a
+//     fixed order, so all replicas compute bit-identical rho, phi and histories with no collective call, no extra launch for
+//     the reduction and no host synchronisation.  Two parities make the buffers safe to reuse: a rank can only write epoch e+2
 //     after its tail of e+1 saw every peer's push of e+1, which those peers issued after their tail of e had read epoch e.
+//     (r01: the kernel's LAST CTA reduced all tiles and pushed the reduced rho -- a serial epilogue of ~9 us on a 150 us step.)
 // Mapping of the peers' buffers: one process driving all GPUs (nufi_b200_group_*) enables direct peer access; one process per
 // GPU (torchrun) exchanges cudaIpcMemHandle_t through the host layer (nufi_b200_peer_export / _attach).
 #include "internal.cuh"
@@ -28,12 +30,12 @@ __global__ void __launch_bounds__(256) peer_gather_kernel(const __grid_constant_
     peer_wait_all(X);
     __syncthreads();
     for (size_t l = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; l < n_nodes; l += static_cast<size_t>(gridDim.x) * blockDim.x)
-        X.rho_full[l] = peer_sum(X, n_nodes, l);
+        X.rho_full[l] = peer_rho(X, l);
 }
 
-size_t data_offset(const Handle *h, int parity, int rank)
+size_t slot_offset(const Handle *h, int parity, int rank)
 {
-    return kPeerFlagBytes + (static_cast<size_t>(parity) * h->px.world + rank) * h->n_nodes * sizeof(double);
+    return kPeerCounterBytes + kPeerHeaderBytes + (static_cast<size_t>(parity) * h->px.world + rank) * h->px.slot_cap * sizeof(double);
 }
 
 } // namespace
@@ -45,7 +47,6 @@ void peer_free(Handle *h)
         for (int p = 0; p < px.world; ++p)
             if (p != px.rank && px.peer_xb[p]) cudaIpcCloseMemHandle(px.peer_xb[p]);
     cudaFree(px.xb);
-    cudaFree(px.d_ticket);
     cudaFree(px.d_status);
     px = PeerState{};
 }
@@ -56,18 +57,19 @@ int peer_alloc(Handle *h, int world)
     peer_free(h);
     PeerState &px = h->px;
     px.world = world;
-    px.xb_bytes = kPeerFlagBytes + 2 * static_cast<size_t>(world) * h->n_nodes * sizeof(double);
+    // slot space per (parity, rank): grid x Tmax x 32 doubles with Tmax = (rpc-1)/rpt + 2 <= n_tiles/grid + 3 (tiles of 32 nodes)
+    const size_t n_tiles = (h->n_nodes + 31) / 32;
+    px.slot_cap = static_cast<size_t>(h->sm_count) * (n_tiles / h->sm_count + 3) * 32;
+    px.xb_bytes = kPeerCounterBytes + kPeerHeaderBytes + 2 * static_cast<size_t>(world) * px.slot_cap * sizeof(double);
     NUFI_CUDA_CHECK(h, cudaMalloc(&px.xb, px.xb_bytes));
     NUFI_CUDA_CHECK(h, cudaMemset(px.xb, 0, px.xb_bytes));
-    NUFI_CUDA_CHECK(h, cudaMalloc(&px.d_ticket, sizeof(unsigned int)));
-    NUFI_CUDA_CHECK(h, cudaMemset(px.d_ticket, 0, sizeof(unsigned int)));
     NUFI_CUDA_CHECK(h, cudaMalloc(&px.d_status, sizeof(int)));
     NUFI_CUDA_CHECK(h, cudaMemset(px.d_status, 0, sizeof(int)));
-    NUFI_CUDA_CHECK(h, cudaDeviceSynchronize()); // the zeroed flags are in place before any peer learns the address
+    NUFI_CUDA_CHECK(h, cudaDeviceSynchronize()); // the zeroed counters are in place before any peer learns the address
     return NUFI_B200_OK;
 }
 
-// Next epoch: pointers for the sender, node ranges for the receiver.
+// Next epoch: pointers for the sender, counter target and slot regions for the receiver.
 int peer_prepare_step(Handle *h)
 {
     PeerState &px = h->px;
@@ -76,23 +78,20 @@ int peer_prepare_step(Handle *h)
     const int parity = static_cast<int>(e & 1);
     PeerPush P{};
     P.world = px.world;
-    P.epoch = e;
-    P.ticket = px.d_ticket;
     for (int p = 0; p < px.world; ++p) {
-        P.data[p] = reinterpret_cast<double *>(px.peer_xb[p] + data_offset(h, parity, px.rank));
-        P.flag[p] = reinterpret_cast<unsigned long long *>(px.peer_xb[p]) + parity * kMaxPeers + px.rank;
+        P.slots[p] = reinterpret_cast<double *>(px.peer_xb[p] + slot_offset(h, parity, px.rank));
+        P.counter[p] = reinterpret_cast<unsigned long long *>(px.peer_xb[p]) + parity * kMaxPeers + px.rank;
+        P.header[p] = reinterpret_cast<PeerHeader *>(px.peer_xb[p] + kPeerCounterBytes) + parity * kMaxPeers + px.rank;
     }
     PeerRecv R{};
     R.world = px.world;
-    R.epoch = e;
-    R.flags = reinterpret_cast<const unsigned long long *>(px.xb) + parity * kMaxPeers;
-    R.data = reinterpret_cast<const double *>(px.xb + data_offset(h, parity, 0));
+    R.counters = reinterpret_cast<const unsigned long long *>(px.xb) + parity * kMaxPeers;
+    R.target = ((e + (e & 1)) / 2) * kPeerUnit; // epochs of this parity so far, kPeerUnit from every rank in each
+    R.headers = reinterpret_cast<const PeerHeader *>(px.xb + kPeerCounterBytes) + parity * kMaxPeers;
+    R.slots = reinterpret_cast<const double *>(px.xb + slot_offset(h, parity, 0));
+    R.slot_cap = px.slot_cap;
     R.rho_full = h->d_rho_full;
     R.status = px.d_status;
-    for (int r = 0; r < px.world; ++r) { // rank r traces velocity nodes r, r+world, ... of EVERY spatial node (see peer_step)
-        if (static_cast<size_t>(r) < h->n_vel) { R.l_first[r] = 0; R.l_last[r] = h->n_nodes - 1; }
-        else { R.l_first[r] = 1; R.l_last[r] = 0; }
-    }
     px.push = P;
     px.recv = R;
     return NUFI_B200_OK;
@@ -183,15 +182,15 @@ int nufi_b200_peer_step(nufi_b200_handle *h, size_t n)
     // a different region of phase space, and regions differ in cost -- trapped orbits replay shared-memory loads -- so the
     // step would wait for the slowest GPU.  The interleaved split gives every GPU a statistically identical sample.)
     if (static_cast<size_t>(px.rank) < hh->n_vel) {
-        hh->fin_push = true;
+        hh->peer_push = true;
         hh->vstride = static_cast<unsigned long long>(px.world);
         hh->voff = static_cast<unsigned long long>(px.rank);
-        rc = nufi_b200_compute_rho(h, n, 0, hh->n_nodes * hh->n_vel); // backtrace, then finish_push_kernel (not finish_rho_kernel)
-        hh->fin_push = false;
+        rc = nufi_b200_compute_rho(h, n, 0, hh->n_nodes * hh->n_vel); // backtrace whose CTAs push their slots to every GPU
+        hh->peer_push = false;
         hh->vstride = 1;
         hh->voff = 0;
     } else {
-        rc = launch_flag_only_push(hh);
+        rc = launch_peer_noop(hh);
     }
     if (rc) return rc;
     return tail_run(hh, n, nullptr, /*from_peer=*/true);

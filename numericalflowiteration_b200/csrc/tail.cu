@@ -286,7 +286,7 @@ struct SmallTailParams
     const double2 *twx, *twy, *twz; // (cos, sin)(2 pi m / N_d)
     const double *rho;              // CPU-convention rho on the device, or nullptr: reduce the backtrace slots (F)
     FinishParams F;
-    PeerRecv X;                     // X.world > 0: rho = 1 + sum over ranks of the peer exchange buffer (waits for the flags)
+    PeerRecv X;                     // X.world > 0: rho from the slots of all ranks in the peer exchange buffer (waits for the counters)
     double *level, *raw1d, *energy_out;
 };
 
@@ -446,7 +446,10 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
     // slot bookkeeping without integer divisions in the load loops: first tile of every backtrace CTA and the CTA range of every
     // tile, tabulated here (one division per thread, hidden behind the backtrace kernel by the programmatic launch)
     __shared__ unsigned short s_tfirst[256], s_blo[128], s_bhi[128];
-    const bool tabulated = !S.rho && !S.X.world && S.F.n_tiles <= 128 && S.F.rpc > 0 && (S.F.rpt * S.F.n_tiles + S.F.rpc - 1) / S.F.rpc <= 256;
+    // (multi-GPU step: S.F holds THIS rank's launch geometry; the peers' headers are compared with it once they have arrived)
+    const bool tabulated = !S.rho && S.F.n_tiles > 0 && S.F.n_tiles <= 128 && S.F.rpc > 0 && (S.F.rpt * S.F.n_tiles + S.F.rpc - 1) / S.F.rpc <= 256;
+    __shared__ int s_same_geometry;
+    if (threadIdx.x == 0) s_same_geometry = tabulated ? 1 : 0;
     if (tabulated) {
         const FinishParams &F = S.F;
         const unsigned n_ctas = (F.rpt * F.n_tiles + F.rpc - 1) / F.rpc;
@@ -464,13 +467,71 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
     //      partial sums over the CTAs that touched its tile, then added in order -- the association of finish_rho_kernel)
     if (S.rho) {
         for (int l = threadIdx.x; l < N; l += blockDim.x) A[l] = make_double2(S.rho[l], 0.0);
-    } else if (S.X.world) { // multi-GPU step: the all-reduce happens here, over peer memory
+    } else if (S.X.world) { // multi-GPU step: the all-reduce happens here -- the slots of ALL ranks, pushed into this GPU's memory
         peer_wait_all(S.X);
+        if (static_cast<int>(threadIdx.x) < S.X.world) { // do all ranks' launches have this rank's geometry?  (they do whenever the
+            // velocity nodes divide evenly over the ranks; then the tables above serve every rank's slots)
+            const unsigned int *hw = reinterpret_cast<const unsigned int *>(S.X.headers + threadIdx.x);
+            const unsigned long long *hl = reinterpret_cast<const unsigned long long *>(S.X.headers + threadIdx.x);
+            const FinishParams &F = S.F;
+            const bool same = __ldcg(hw + 0) == F.rpt && __ldcg(hw + 1) == F.rpc && __ldcg(hw + 2) == F.Tmax && __ldcg(hw + 3) == F.n_tiles &&
+                              __ldcg(hw + 4) == F.TN && __ldcg(hl + 4) == F.l_first && __ldcg(hl + 5) == F.l_last;
+            if (!same) s_same_geometry = 0;
+        }
         __syncthreads();
-        for (int l = threadIdx.x; l < N; l += blockDim.x) {
-            const double r = peer_sum(S.X, N, l);
-            S.X.rho_full[l] = r;
-            A[l] = make_double2(r, 0.0);
+        TAIL_MARK(10); // peer mode: [9 -> 10] = wait for the peers' counters, [10 -> 1] = slot reduction over all ranks
+        const double dV = S.F.dV;
+        const bool fast = s_same_geometry != 0;
+        const unsigned tn_log2 = 31 - __clz(S.F.TN);
+        // one of the 8 strided partial sums of node l over the slots of all ranks (rank 0's CTAs b_lo+w, b_lo+w+8, ..., then
+        // rank 1's, ...): table-driven when every rank shares this rank's geometry, else from each rank's own header
+        auto rank_sum = [&](int l, int w) {
+            if (!fast) return peer_slot_sum(S.X, l, w);
+            const FinishParams &F = S.F;
+            const unsigned tile = static_cast<unsigned>(l) >> tn_log2, lane = static_cast<unsigned>(l) & (F.TN - 1);
+            const unsigned b_lo = s_blo[tile], b_hi = s_bhi[tile];
+            double sum = 0;
+            for (int r = 0; r < S.X.world; ++r) {
+                const double *slots = S.X.slots + static_cast<size_t>(r) * S.X.slot_cap;
+                for (unsigned b = b_lo + w; b <= b_hi; b += 32) {
+                    double v[4];
+#pragma unroll
+                    for (unsigned u = 0; u < 4; ++u) {
+                        const unsigned bb = b + 8 * u;
+                        v[u] = bb <= b_hi ? __ldcg(slots + (static_cast<size_t>(bb) * F.Tmax + (tile - s_tfirst[bb])) * 32 + lane) : 0.0;
+                    }
+                    sum = (((sum + v[0]) + v[1]) + v[2]) + v[3]; // + 0.0 is exact: the order of one-by-one addition
+                }
+            }
+            return sum;
+        };
+        if (8 * N <= 2 * kSmallPart) { // the 8 partial sums of a node spread over up to 8 threads, combined in order afterwards
+            int G = 1;
+            while (2 * G * N <= static_cast<int>(blockDim.x) && G < 8) G *= 2;
+            double *ps = reinterpret_cast<double *>(part); // [8][N]
+            for (int it = threadIdx.x; it < N * G; it += blockDim.x) {
+                int l = it, g = 0;
+                while (l >= N) { l -= N; ++g; }
+                for (int w = g; w < 8; w += G) ps[w * N + l] = rank_sum(l, w);
+            }
+            __syncthreads();
+            for (int l = threadIdx.x; l < N; l += blockDim.x) {
+                double tot = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) tot += ps[w * N + l];
+                const double r = 1 - dV * tot;
+                S.X.rho_full[l] = r;
+                A[l] = make_double2(r, 0.0);
+            }
+        } else {
+            for (int l = threadIdx.x; l < N; l += blockDim.x) {
+                double tot = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) tot += rank_sum(l, w);
+                const double r = 1 - dV * tot;
+                S.X.rho_full[l] = r;
+                A[l] = make_double2(r, 0.0);
+            }
         }
     } else {
         const FinishParams &F = S.F;
@@ -782,6 +843,12 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full, bool from_peer)
         if (from_peer) {
             S.rho = nullptr;
             S.X = h->px.recv;
+            const PeerHeader &H = h->px.push.hdr; // this rank's launch geometry (n_tiles = 0: this rank had no work)
+            S.F.rpt = H.rpt; S.F.rpc = H.rpc; S.F.Tmax = H.Tmax; S.F.n_tiles = H.n_tiles; S.F.TN = H.TN ? H.TN : 32;
+            S.F.l_first = H.l_first; S.F.l_last = H.l_last;
+            S.F.dV = H.n_tiles ? H.dV : h->dim == 1 ? (c.u_max - c.u_min) / c.Nu
+                                 : (h->dim == 2 ? (c.u_max - c.u_min) / c.Nu * ((c.v_max - c.v_min) / c.Nv)
+                                                : (c.u_max - c.u_min) / c.Nu * ((c.v_max - c.v_min) / c.Nv) * ((c.w_max - c.w_min) / c.Nw));
         } else if (d_rho_full) {
             S.rho = d_rho_full;
         } else {
