@@ -42,6 +42,7 @@ SMEM_BYTES_PER_POINT_STEP = {1: 24.0, 2: 128.0, 3: 512.0}  # coefficients a poin
 SMEM_BYTES_PER_CLK_SM = 128.0  # shared-memory data pipe; tools/microbench.cu measures 125-127 on this GPU
 L2_FLUSH_BYTES = 256 << 20
 RHO_TOL = 1e-10
+ALIGN_RANKS = True  # N > 1: a stream-ordered NCCL barrier between the (untimed) L2 flush and every timed step
 
 
 def make_workload(name: str, n_gpus: int, scaling: str = "weak"):
@@ -318,11 +319,16 @@ class GpuRunner:
         self.s.close()
 
 
-def timed_region(runner, n, steps, warmup, flush, torch, dist, sampler=None):
+def timed_region(runner, n, steps, warmup, flush, torch, dist, sampler=None, align=None):
     """`warmup` untimed steps, then `steps` fused steps at depth n, each bracketed by a CUDA event pair on the stream the
     library launches on, with an (untimed) L2 flush in front of each.  Returns (sum of step times in ms, max over ranks; launches)."""
     s, st = runner.s, runner.stream
-    for _ in range(warmup):
+    for _ in range(warmup):  # untimed, same shape as the timed iterations below
+        with torch.cuda.stream(st):
+            if flush is not None:
+                flush.fill_(1.0)
+            if align is not None:
+                dist.all_reduce(align)
         runner.step(n)
     st.synchronize()
     if runner.world > 1:
@@ -334,7 +340,10 @@ def timed_region(runner, n, steps, warmup, flush, torch, dist, sampler=None):
     with ctx:
         for a, b in ev:
             with torch.cuda.stream(st):
-                flush.fill_(1.0)  # L2 flush, untimed
+                if flush is not None:
+                    flush.fill_(1.0)  # L2 flush, untimed
+                if align is not None:  # untimed: the ranks leave the flush together (its duration jitters by microseconds), as
+                    dist.all_reduce(align)  # they do in a run without flushes, where every step ends with the exchange
             a.record(st)
             runner.step(n)
             b.record(st)
@@ -343,7 +352,9 @@ def timed_region(runner, n, steps, warmup, flush, torch, dist, sampler=None):
             dist.barrier()
         torch.cuda.synchronize()
     launches = s.launches - l0
-    t_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    per_step = [float(a.elapsed_time(b)) for a, b in ev]
+    timed_region.last_per_step_ms = per_step
+    t_ms = float(sum(per_step))
     if runner.world > 1:
         tt = torch.tensor([t_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -351,17 +362,20 @@ def timed_region(runner, n, steps, warmup, flush, torch, dist, sampler=None):
     return t_ms, int(launches)
 
 
-def measure_gpu(runner, n, steps, warmup, flush, torch, dist, sampler=None):
+def measure_gpu(runner, n, steps, warmup, flush, torch, dist, sampler=None, align=None):
     """Two timed regions of the same K steps: (1) as a user runs it -> `value`; (2) with the library's per-launch CUDA
     event pair around every backtrace kernel -> the kernel's average duration for the roofline (the events sit between
     the kernel and the field tail and keep the tail from launching programmatically behind it, so region 2 is slightly
     slower per step; its own step time is reported beside the kernel time)."""
     s = runner.s
     s.set_kernel_timing(False)
-    t_ms, launches = timed_region(runner, n, steps, warmup, flush, torch, dist, sampler)
+    if align is None and runner.world > 1 and ALIGN_RANKS:
+        align = torch.zeros(1, device="cuda")
+    t_ms, launches = timed_region(runner, n, steps, warmup, flush, torch, dist, sampler, align)
+    per_step = list(timed_region.last_per_step_ms)
     s.set_kernel_timing(True)
     s.backtrace_time(reset=True)
-    t2_ms, _ = timed_region(runner, n, steps, 3, flush, torch, dist)
+    t2_ms, _ = timed_region(runner, n, steps, 3, flush, torch, dist, None, align)
     bt_total, bt_count = s.backtrace_time(reset=True)  # warm-up launches included: same kernel, same inputs
     s.set_kernel_timing(False)
     bt_ms = bt_total / max(bt_count, 1)
@@ -370,7 +384,8 @@ def measure_gpu(runner, n, steps, warmup, flush, torch, dist, sampler=None):
         g = [torch.zeros(1, device="cuda", dtype=torch.float64) for _ in range(runner.world)]
         dist.all_gather(g, torch.tensor([bt_ms], device="cuda", dtype=torch.float64))
         bt_all = [float(x.item()) for x in g]
-    return {"t_ms": t_ms, "t_ms_kernel_timing": t2_ms, "bt_ms": bt_ms, "bt_ms_per_rank": bt_all, "launches": int(launches)}
+    return {"t_ms": t_ms, "t_ms_kernel_timing": t2_ms, "bt_ms": bt_ms, "bt_ms_per_rank": bt_all, "launches": int(launches),
+            "per_step_ms": per_step}
 
 
 class _Null:
@@ -597,7 +612,9 @@ def run_gpu_arm(args):
     runner = GpuRunner(conf, f0, rank, world, torch, dist, exchange=args.exchange)
     s = runner.s
     nq = n_quad(conf)
-    flush = torch.empty(L2_FLUSH_BYTES // 8, dtype=torch.float64, device="cuda")
+    flush = None if args.no_flush else torch.empty(L2_FLUSH_BYTES // 8, dtype=torch.float64, device="cuda")
+    global ALIGN_RANKS
+    ALIGN_RANKS = not args.no_align
 
     t0 = time.perf_counter()
     free_run(runner, n)  # levels 0..n-1 on the device
@@ -665,7 +682,10 @@ def run_gpu_arm(args):
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "depth_n": n, "point_steps_per_step": psteps, "n_quad": nq,
                        "history": f"built on the device by {n} free-running fused steps ({t_hist:.2f} s)",
-                       "l2": "flushed between timed steps (256 MiB fill, untimed; steps timed individually with CUDA events)",
+                       "l2": ("NOT flushed (experiment)" if args.no_flush else
+                              "flushed between timed steps (256 MiB fill, untimed; steps timed individually with CUDA events)" +
+                              ("; ranks aligned by a stream-ordered NCCL barrier between the flush and each timed step (untimed)"
+                               if world > 1 and ALIGN_RANKS else "")),
                        "parallelism": (f"quadrature points sharded over {world} GPU(s); rho exchange: " +
                                        ("stores into NVLink peer memory fused into the slot-reduction and tail kernels (no collective call)"
                                         if runner.exchange == "peer-memory" else "NCCL all-reduce")) if world > 1 else "1 GPU",
@@ -676,6 +696,8 @@ def run_gpu_arm(args):
                     "path": "upload_phi(n-1) -> compute_rho -> download_rho -> solve_interpolate_host, host buffers, wall clock"},
             "gpu_launches": m["launches"], "clocks": sampler.summary() if sampler else None,
             "s_per_time_step": m["t_ms"] / args.steps * 1e-3,
+            "step_ms_rank0": {"min": min(m["per_step_ms"]), "median": float(np.median(m["per_step_ms"])), "max": max(m["per_step_ms"]),
+                              "first_10": [round(x, 4) for x in m["per_step_ms"][:10]]},
         }
     runner.close()
     del runner, s
@@ -742,6 +764,8 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the partial rho is exchanged (peer = stores into NVLink peer memory fused into the kernels)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="experiment: no L2 flush between the timed steps (not a valid bench line)")
+    ap.add_argument("--no-align", action="store_true", help="N > 1: no rank alignment between the L2 flush and the timed step")
     ap.add_argument("--no-extras", dest="extras", action="store_false")
     ap.add_argument("--no-full-run", dest="full_run", action="store_false")
     args = ap.parse_args()

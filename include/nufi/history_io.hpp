@@ -40,6 +40,12 @@ inline size_t stride_t(const header &h)
     return (h.Nx + o) * (h.dim >= 2 ? h.Ny + o : 1) * (h.dim >= 3 ? h.Nz + o : 1);
 }
 
+// does a header describe histories of the running configuration?  (dim, order and grid must agree before upload_history)
+inline bool matches(const header &h, unsigned dim, unsigned order, size_t Nx, size_t Ny = 1, size_t Nz = 1)
+{
+    return h.dim == dim && h.order == order && h.Nx == Nx && (dim < 2 || h.Ny == Ny) && (dim < 3 || h.Nz == Nz);
+}
+
 inline void write_binary(const std::string &path, const header &h_in, const double *coeffs)
 {
     header h = h_in;
@@ -59,6 +65,19 @@ inline header read_binary(const std::string &path, std::vector<double> &coeffs)
     header h;
     f.read(reinterpret_cast<char *>(&h), sizeof(h));
     if (!f || std::memcmp(h.magic, "NUFIB200", 8) != 0 || h.version != 1) throw std::runtime_error("history_io: not a nufi-b200 history: " + path);
+    // do not trust the header: every field bounded before it sizes an allocation (a corrupt or foreign file must not wrap the
+    // product or ask for petabytes); callers compare the header with their running config (matches) before upload_history
+    const size_t lim = size_t(1) << 20;
+    if (h.dim < 1 || h.dim > 3 || h.order < 1 || h.order > 8 || h.Nx < 1 || h.Nx > lim || (h.dim >= 2 && (h.Ny < 1 || h.Ny > lim)) ||
+        (h.dim >= 3 && (h.Nz < 1 || h.Nz > lim)) || h.n_levels > lim)
+        throw std::runtime_error("history_io: implausible header in " + path);
+    const long double total = static_cast<long double>(h.n_levels) * static_cast<long double>(stride_t(h));
+    if (total > static_cast<long double>(size_t(1) << 37)) throw std::runtime_error("history_io: header of " + path + " asks for more than 1 TiB");
+    f.seekg(0, std::ios::end);
+    const std::streamoff have = f.tellg();
+    if (have < 0 || static_cast<long double>(have) < static_cast<long double>(sizeof(h)) + total * sizeof(double))
+        throw std::runtime_error("history_io: truncated history: " + path);
+    f.seekg(sizeof(h), std::ios::beg);
     coeffs.resize(h.n_levels * stride_t(h));
     f.read(reinterpret_cast<char *>(coeffs.data()), static_cast<std::streamsize>(sizeof(double) * coeffs.size()));
     if (!f) throw std::runtime_error("history_io: truncated history: " + path);

@@ -194,9 +194,11 @@ int nufi_b200_field_tail_device(nufi_b200_handle *h, size_t n, const double *d_r
  *      buffer, returns a 64-byte CUDA IPC handle), the host layer all-gathers the handles (rank order), every rank calls
  *      peer_attach.  peer_step(n) = backtrace of this rank's share of the quadrature points -- velocity nodes rank, rank+world,
  *      ... of every spatial node, so all GPUs trace statistically identical samples of phase space (the reference's contiguous
- *      flat-q split, nufi/cuda_scheduler.hpp:88-111, stays available through compute_rho(q_begin, q_end)) -> slot reduction
- *      that STORES the partial rho into every GPU's buffer and releases a
- *      flag there -> field tail that acquires all ranks' flags and adds the contributions in rank order (bit-identical on all
+ *      flat-q split, nufi/cuda_scheduler.hpp:88-111, stays available through compute_rho(q_begin, q_end)); inside that kernel the
+ *      last CTA to finish a tile of 32 spatial nodes adds the tile's partial sums in a fixed order and STORES them into every
+ *      GPU's buffer, each 8-byte word carrying the step's epoch beside 32 bits of payload -- no fence to system scope, no flag, no
+ *      serial epilogue on the sender -> field tail that adds the ranks' sums in rank order, polling each word until it carries
+ *      this step's epoch, without waiting for its own GPU's backtrace grid to retire (bit-identical on all
  *      GPUs) -> level n.  Asynchronous, no collective call, no host synchronisation.  All ranks must call peer_step the same
  *      number of times; synchronise all ranks (host barrier) before peer_detach / destroy.  peer_status: blocking; *timed_out
  *      = 1 if a wait for a peer's flag ever gave up (a rank died or skipped a step; results are then invalid). ---- */

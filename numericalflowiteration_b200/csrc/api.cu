@@ -68,7 +68,7 @@ void free_all(Handle *h)
     tail_destroy(h);
     peer_free(h);
     cudaFree(h->d_hist); cudaFree(h->d_raw);
-    cudaFree(h->d_rho_partial); cudaFree(h->d_rho_full); cudaFree(h->d_partials);
+    cudaFree(h->d_rho_partial); cudaFree(h->d_rho_full); cudaFree(h->d_partials); cudaFree(h->d_partials_ll); cudaFree(h->d_ll_status);
     cudaFree(h->d_metrics); cudaFree(h->d_mpartials); cudaFree(h->d_energy); cudaFree(h->d_stage); cudaFree(h->d_done);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->h_up) cudaFreeHost(h->h_up);
@@ -190,6 +190,8 @@ int create_common(const nufi_b200_config3d &c, int dim, int order, const nufi_b2
     CREATE_CHECK(cudaMalloc(&h->d_stage, h->stride_t * sizeof(double)));
     CREATE_CHECK(cudaMalloc(&h->d_done, sizeof(unsigned int)));
     CREATE_CHECK(cudaMemsetAsync(h->d_done, 0, sizeof(unsigned int), h->stream));
+    CREATE_CHECK(cudaMalloc(&h->d_ll_status, sizeof(int)));
+    CREATE_CHECK(cudaMemsetAsync(h->d_ll_status, 0, sizeof(int), h->stream));
     h->h_pinned_cap = h->stride_t > h->n_nodes ? h->stride_t : h->n_nodes;
     if (h->h_pinned_cap < c.Nt + 1) h->h_pinned_cap = c.Nt + 1;
     CREATE_CHECK(cudaMallocHost(&h->h_pinned, h->h_pinned_cap * sizeof(double)));

@@ -31,8 +31,10 @@ namespace nufi_b200
 namespace
 {
 
-// Adds the per-(CTA, tile) slots of each tile in a fixed order.  One block (8 warps) per tile of 32 nodes.
-__global__ void __launch_bounds__(256) finish_rho_kernel(const __grid_constant__ FinishParams F)
+// Adds the per-(CTA, tile) slots of each tile in a fixed order.  One block (8 warps) per tile of 32 nodes.  Multi-GPU step on a
+// grid too large for the one-CTA tail (X.world > 0): the sums also go into every GPU's exchange buffer (NVLink stores of
+// self-validating words, internal.cuh), where peer_gather_kernel adds them in rank order.
+__global__ void __launch_bounds__(256) finish_rho_kernel(const __grid_constant__ FinishParams F, const __grid_constant__ PeerPush X)
 {
     __shared__ double part[8][32];
     pdl_wait();
@@ -57,22 +59,18 @@ __global__ void __launch_bounds__(256) finish_rho_kernel(const __grid_constant__
         if (static_cast<unsigned>(lane) < F.TN && l <= F.l_last) {
             F.rho_partial[l] = -F.dV * tot;
             if (F.rho_full) F.rho_full[l] = 1 - F.dV * tot;
+            for (int p = 0; p < X.world; ++p) peer_store_double(X.rho[p] + l, tot, X.flag);
         }
     }
 }
 
-// A rank without work in a multi-GPU step (more ranks than velocity nodes) still owes every GPU its counter units and an
-// (empty) header for this epoch.
-__global__ void peer_noop_kernel(const __grid_constant__ PeerPush X)
+// A rank without work in a multi-GPU step (more ranks than velocity nodes) still owes every GPU its (zero) sums of this epoch.
+__global__ void __launch_bounds__(256) peer_noop_kernel(const __grid_constant__ PeerPush X, size_t n_nodes)
 {
     pdl_wait();
     pdl_trigger();
-    if (threadIdx.x == 0) {
-        for (int p = 0; p < X.world; ++p) *X.header[p] = X.hdr;
-        __threadfence_system();
-        for (int p = 0; p < X.world; ++p)
-            asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(X.counter[p]), "l"(kPeerUnit) : "memory");
-    }
+    for (size_t l = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; l < n_nodes; l += static_cast<size_t>(gridDim.x) * blockDim.x)
+        for (int p = 0; p < X.world; ++p) peer_store_double(X.rho[p] + l, 0.0, X.flag);
 }
 
 __global__ void finish_metrics_kernel(const double *mpartials, unsigned grid, double *metrics)
@@ -349,47 +347,54 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     const unsigned threads = (P.W + (staged ? 1 : 0)) * 32;
     const size_t smem_bytes = kSmemFixed + (staged ? static_cast<size_t>(P.stages) * P.stage_bytes : 0);
 
-    // ---- slots: one per (CTA, tile it touches); every slot the finish kernel reads is written by its CTA
-    const bool push = !metrics && h->peer_push; // multi-GPU step: the slots live in the exchange buffers of all GPUs
-    if (push) {
+    // ---- slots: one per (CTA, tile it touches); every slot the reduction reads is written by its CTA
+    const bool push = !metrics && h->peer_push; // this GPU's share of a multi-GPU step: the sums go to every GPU
+    const bool all_nodes = q_begin == 0 && q_end == h->n_nodes * h->n_vel; // every node's value gets written
+    const bool whole = all_nodes && P.vstride == 1;                         // ... and it is the complete sum
+    if (push && !all_nodes) return fail(h, NUFI_B200_ERR_ARG, "peer step: the backtrace must cover every spatial node");
+    // who adds the slots: the fused one-CTA tail behind this launch (fused step on a small grid: it polls self-validating slots
+    // instead of waiting for this grid to retire), finish_rho_kernel (many tiles, or a multi-GPU step on a large grid), or this
+    // kernel's own last-CTA epilogue (compute_rho)
+    const bool tail_reduces = !metrics && ((defer_finish && whole) || push) && tail_is_small(h);
+    if (!metrics) {
         const size_t need = static_cast<size_t>(grid) * P.Tmax * 32;
-        if (need > h->px.slot_cap)
-            return fail(h, NUFI_B200_ERR_ARG, "peer step: this launch shape needs more slot space than the exchange buffer holds (nodes per tile forced below 32?)");
-    } else if (!metrics) {
-        const size_t need = static_cast<size_t>(grid) * P.Tmax * 32;
-        if (need > h->partials_cap) {
-            if (h->d_partials) cudaFree(h->d_partials);
-            h->d_partials = nullptr;
-            h->partials_cap = 0;
-            if (cudaMalloc(&h->d_partials, need * sizeof(double)) != cudaSuccess)
-                return fail(h, NUFI_B200_ERR_ALLOC, "cudaMalloc of the rho partial slots failed");
-            h->partials_cap = need;
+        if (tail_reduces) {
+            if (need > h->partials_ll_cap) {
+                if (h->d_partials_ll) cudaFree(h->d_partials_ll);
+                h->d_partials_ll = nullptr;
+                h->partials_ll_cap = 0;
+                if (cudaMalloc(&h->d_partials_ll, need * sizeof(uint4)) != cudaSuccess)
+                    return fail(h, NUFI_B200_ERR_ALLOC, "cudaMalloc of the rho partial slots failed");
+                NUFI_CUDA_CHECK(h, cudaMemsetAsync(h->d_partials_ll, 0, need * sizeof(uint4), h->stream)); // epoch 0 = "nothing yet"
+                h->partials_ll_cap = need;
+            }
+            if (++h->slot_epoch == 0) h->slot_epoch = 1;
+            P.slots_ll = h->d_partials_ll;
+            P.slot_flag = h->slot_epoch;
+        } else {
+            if (need > h->partials_cap) {
+                if (h->d_partials) cudaFree(h->d_partials);
+                h->d_partials = nullptr;
+                h->partials_cap = 0;
+                if (cudaMalloc(&h->d_partials, need * sizeof(double)) != cudaSuccess)
+                    return fail(h, NUFI_B200_ERR_ALLOC, "cudaMalloc of the rho partial slots failed");
+                h->partials_cap = need;
+            }
+            P.slots = h->d_partials;
         }
-        P.slots = h->d_partials;
     } else {
         P.mpartials = h->d_mpartials;
         NUFI_CUDA_CHECK(h, cudaMemsetAsync(h->d_mpartials, 0, sizeof(double) * 4 * grid, h->stream));
     }
 
-    // ---- slot reduction: by the fused tail (defer), else by the kernel's own last-CTA epilogue (optionally pushing to the peers)
     EpilogueParams E{};
-    bool tail_reduces = false;
-    if (push) {
-        E.mode = 3;
-        E.n_active = (P.R + P.rpc - 1) / P.rpc;
-        E.X = h->px.push;
-        PeerHeader &H = E.X.hdr;
-        H.rpt = P.rpt; H.rpc = P.rpc; H.Tmax = P.Tmax; H.n_tiles = P.n_tiles; H.TN = P.TN; H.n_ctas = E.n_active;
-        H.dV = h->dim == 1 ? P.du : (h->dim == 2 ? P.du * P.dv : P.du * P.dv * P.dw); // rho.hpp:145, 307, 459
-        H.l_first = P.l_first; H.l_last = P.l_last;
-        h->px.push.hdr = H; // the tail tabulates its slot loads from this rank's geometry before the peers' headers arrive
-        h->fin_pending = false;
-    } else if (!metrics) {
+    if (!metrics) {
         FinishParams F{};
-        F.slots = h->d_partials;
+        F.slots = P.slots;
+        F.slots_ll = P.slots_ll;
+        F.slot_flag = P.slot_flag;
+        F.status = h->d_ll_status;
         F.rho_partial = h->d_rho_partial;
-        const bool all_nodes = q_begin == 0 && q_end == h->n_nodes * h->n_vel; // every node's value gets written
-        const bool whole = all_nodes && P.vstride == 1;                         // ... and it is the complete sum
         F.rho_full = whole ? h->d_rho_full : nullptr;
         F.dV = h->dim == 1 ? P.du : (h->dim == 2 ? P.du * P.dv : P.du * P.dv * P.dw); // rho.hpp:145, 307, 459
         F.l_first = P.l_first; F.l_last = P.l_last;
@@ -398,10 +403,10 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
         F.TN = P.TN;
         if (!all_nodes) NUFI_CUDA_CHECK(h, cudaMemsetAsync(h->d_rho_partial, 0, sizeof(double) * h->n_nodes, h->stream));
         h->fin = F;
-        tail_reduces = defer_finish && whole;
         h->fin_pending = tail_reduces;
-        // many tiles (TN < 32 on a large grid): the one-CTA epilogue would serialise them; use the multi-block finish kernels
-        const bool epilogue = P.n_tiles <= 256;
+        // many tiles (TN < 32 on a large grid): the one-CTA epilogue would serialise them; use the multi-block finish kernel,
+        // which is also the one that pushes to the peers
+        const bool epilogue = P.n_tiles <= 256 && !push;
         if (!tail_reduces && !epilogue) {
             h->fin_pending = true; // launch_finish() below runs finish_rho_kernel
         } else if (!tail_reduces) {
@@ -508,9 +513,10 @@ int launch_sample_field(Handle *h, const double *d_ref_level, int der, size_t np
 
 int launch_peer_noop(Handle *h)
 {
-    h->px.push.hdr = PeerHeader{}; // n_tiles = 0: nothing to add for this rank
     PeerPush X = h->px.push;
-    NUFI_CUDA_CHECK(h, launch_chained(h, peer_noop_kernel, dim3(1), dim3(32), 0, X));
+    size_t blocks = (h->n_nodes + 255) / 256;
+    if (blocks > 148) blocks = 148;
+    NUFI_CUDA_CHECK(h, launch_chained(h, peer_noop_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, X, h->n_nodes));
     h->launches += 1;
     return NUFI_B200_OK;
 }
@@ -518,7 +524,9 @@ int launch_peer_noop(Handle *h)
 int launch_finish(Handle *h)
 {
     if (!h->fin_pending) return NUFI_B200_OK;
-    NUFI_CUDA_CHECK(h, launch_chained(h, finish_rho_kernel, dim3(h->fin.n_tiles), dim3(256), 0, h->fin));
+    PeerPush X{}; // world 0 unless this is the large-grid leg of a multi-GPU step
+    if (h->peer_push) X = h->px.push;
+    NUFI_CUDA_CHECK(h, launch_chained(h, finish_rho_kernel, dim3(h->fin.n_tiles), dim3(256), 0, h->fin, X));
     NUFI_CUDA_CHECK(h, cudaGetLastError());
     h->fin_pending = false;
     h->launches += 1;

@@ -600,11 +600,8 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
             for (unsigned off = 16; off >= P.TN; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
             const size_t slot = (static_cast<size_t>(blockIdx.x) * P.Tmax + (tile - t_first)) * 32 + lane;
             const double val = static_cast<unsigned>(lane) < P.TN ? sum : 0.0;
-            if (E.mode == 3) { // multi-GPU step: the slot goes straight into every GPU's exchange buffer (NVLink stores; own GPU included)
-                for (int p = 0; p < E.X.world; ++p) E.X.slots[p][slot] = val;
-            } else {
-                P.slots[slot] = val;
-            }
+            if (P.slots_ll) peer_store_double(P.slots_ll + slot, val, P.slot_flag); // fused step: the resident tail polls for it
+            else P.slots[slot] = val;
         }
         consumer_sync(W * 32);
         acc = 0;
@@ -771,28 +768,7 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
 
     if (!P.metrics) {
         flush_tile(cur_tile);
-        if (E.mode == 3) { // ---- multi-GPU step: this CTA's slots are on their way to every GPU; sign off on the peers' counters
-            // (flush_tile ended with a barrier over the consumer warps: thread 0 has observed every remote slot store of this CTA, so
-            //  its one cumulative system-scope fence orders them all before the counter updates -- the release side of the tail's
-            //  ld.acquire.sys.)  CTA 0 also publishes the launch geometry and tops the count up to kPeerUnit per rank and epoch.
-            if (threadIdx.x == 0) {
-#ifdef NUFI_TAIL_TIMING
-                const long long tk0 = clock64();
-#endif
-                if (blockIdx.x == 0)
-                    for (int p = 0; p < E.X.world; ++p) *E.X.header[p] = E.X.hdr;
-                __threadfence_system();
-#ifdef NUFI_TAIL_TIMING
-                const long long tk1 = clock64();
-#endif
-                const unsigned long long inc = blockIdx.x == 0 ? kPeerUnit - (E.n_active - 1) : 1ull;
-                for (int p = 0; p < E.X.world; ++p)
-                    asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(E.X.counter[p]), "l"(inc) : "memory");
-#ifdef NUFI_TAIL_TIMING
-                if (blockIdx.x == 0 || blockIdx.x == 77) printf("push sign-off CTA %u (cycles): fence.sys %lld  counter adds %lld\n", blockIdx.x, tk1 - tk0, clock64() - tk1);
-#endif
-            }
-        } else if (E.mode) { // ---- epilogue: the last CTA to arrive reduces the slots of all tiles
+        if (E.mode) { // ---- epilogue: the last CTA to arrive reduces the slots of all tiles
             // (flush_tile ended with a barrier over the consumer warps: thread 0 has observed every slot store of this CTA, so its
             //  one cumulative fence orders them all before the ticket -- the pattern of cooperative-groups grid sync.  A fence in
             //  every thread costs microseconds here, and tens of them at system scope below.)

@@ -51,6 +51,8 @@ struct BtParams
     unsigned int Tmax;               // slots per CTA (tiles one CTA can touch)
     int interleave;                  // 1: warp-unit jc = jr + warp*rpt, point i of a thread at velocity jc + i*upt (balanced mix)
     double *slots;                   // [grid][Tmax][32]                (rho)
+    uint4 *slots_ll;                 // non-null: the slots go here instead, each as a self-validating word pair carrying slot_flag
+    unsigned int slot_flag;          //           (the fused tail polls them instead of waiting for this grid to retire)
     double *mpartials;               // [grid][4]                       (metrics)
     double mweight;
     // staged variant: shared-memory ring of `stages` stages, each a chunk of Lc consecutive levels
@@ -73,6 +75,9 @@ struct SampleParams
 struct FinishParams
 {
     const double *slots;
+    const uint4 *slots_ll; // non-null: self-validating slots (see BtParams::slots_ll); polled until they carry slot_flag
+    unsigned int slot_flag;
+    int *status;           // set to 1 if a polled word never arrived (bounded spin)
     double *rho_partial; // GPU convention: -dV * sum
     double *rho_full;    // CPU convention: 1 - dV * sum  (may be nullptr)
     double dV;
@@ -82,50 +87,41 @@ struct FinishParams
 };
 
 // ----------------------------------------------------------------------------------------------
-// Peer exchange of the partial rho over NVLink/NVSwitch peer memory (peer.cu).  What travels are the backtrace kernel's own
-// per-(CTA, tile) SLOTS: every GPU owns an exchange buffer
-//   [counters: 2 parities x kMaxPeers x u64][headers: 2 x kMaxPeers x PeerHeader][slots: 2 x world x slot_cap doubles]
-// mapped into all peers (one process: cudaDeviceEnablePeerAccess; one process per GPU: CUDA IPC).  Per step with epoch e
-// (parity e&1) every CTA of rank r STORES each slot it finishes straight into region [e&1][r] of EVERY GPU (its own included),
-// and when it is done fences once and adds to counter[e&1][r] on every GPU; CTA 0 also writes the launch geometry (header) and
-// tops the counter up so that every rank contributes exactly kPeerUnit per epoch whatever its CTA count.  No last-CTA
-// reduction, no serial epilogue: the kernel ends when its CTAs end.  The field tail of every GPU acquires the world counters
-// and adds all ranks' slots in a fixed order (bit-identical on every GPU).
+// Self-validating words ("low latency" encoding) and the peer exchange of the partial rho over NVLink/NVSwitch peer memory.
+//
+// A double travels as one 16-byte vector store {lo, epoch, hi, epoch}: every 8-byte half carries 32 bits of payload and the
+// 32-bit epoch of the step (an aligned 8-byte store is delivered whole), so a reader needs neither a flag nor a fence on the
+// writer's side, and need not wait for the writing grid to retire: it polls the words it is about to add until they carry this
+// step's epoch.  Two uses:
+//  (1) the backtrace kernel's per-(CTA, tile) slots in a fused step (BtParams::slots_ll): the one-CTA field tail, resident
+//      beside the backtrace grid since its start (programmatic dependent launch), adds them in the fixed order of
+//      finish_rho_kernel as they land -- no kernel-boundary wait on the step's critical path;
+//  (2) the exchange between GPUs: every GPU owns a buffer [2 parities][world][n_nodes] x 16 B mapped into all peers (one process:
+//      cudaDeviceEnablePeerAccess; one process per GPU: CUDA IPC).  Per step with epoch e (parity e&1) the tail (large grids:
+//      finish_rho_kernel) of rank r STORES its per-node sums straight into region [e&1][r] of every other GPU as soon as it has
+//      them, then adds all ranks' sums in rank order (bit-identical on every GPU), polling the peers' words.  No collective call,
+//      no system-scope fence (3.8 us measured), no flag, no extra launch.  Two parities make the buffers safe to reuse: a rank
+//      writes epoch e+2 only after its tail of e+1 has read every peer's words of e+1, which those peers pushed after their
+//      tails of e had finished reading epoch e.
 // ----------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 16;
-constexpr unsigned long long kPeerUnit = 1ull << 20; // counter units one rank contributes per epoch (> any CTA count)
 
-struct PeerHeader // launch geometry of one rank's backtrace kernel: where its slots are and how to add them (64 bytes)
+struct PeerPush // sender side (tail_small_kernel / finish_rho_kernel)
 {
-    unsigned int rpt, rpc, Tmax, n_tiles, TN, n_ctas;
-    double dV;
-    unsigned long long l_first, l_last;
-    unsigned long long pad[2];
-};
-static_assert(sizeof(PeerHeader) == 64, "PeerHeader is 64 bytes");
-
-constexpr size_t kPeerCounterBytes = 2 * kMaxPeers * sizeof(unsigned long long);
-constexpr size_t kPeerHeaderBytes = 2 * kMaxPeers * sizeof(PeerHeader);
-
-struct PeerPush // sender side (backtrace kernel, epilogue mode 3)
-{
-    double *slots[kMaxPeers];               // region [e&1][my rank] inside every GPU's exchange buffer
-    unsigned long long *counter[kMaxPeers]; // counter[e&1][my rank] inside every GPU's exchange buffer
-    PeerHeader *header[kMaxPeers];          // header[e&1][my rank] inside every GPU's exchange buffer
-    int world;
-    PeerHeader hdr;                         // this launch's geometry (written by CTA 0)
+    uint4 *rho[kMaxPeers];     // region [e&1][my rank] inside every GPU's exchange buffer: one uint4 {lo, epoch, hi, epoch} per node
+    int world, rank;           // world 0: not a peer step
+    unsigned int flag;         // this step's epoch (never 0: the buffers start zeroed)
 };
 
 struct PeerRecv // receiver side (tail_small_kernel / peer_gather_kernel)
 {
-    int world;                              // 0: not a peer step
-    const unsigned long long *counters;     // local counter[e&1][0..world)
-    unsigned long long target;              // value every counter reaches once its rank's epoch-e pushes have all landed
-    const PeerHeader *headers;              // local header[e&1][0..world)
-    const double *slots;                    // local region [e&1][0]; rank r at + r * slot_cap
-    size_t slot_cap;                        // doubles per (parity, rank) region
-    double *rho_full;                       // CPU-convention rho (1 - dV * sum) for later downloads
-    int *status;                            // set to 1 if a counter never arrived (bounded spin)
+    int world;                 // 0: not a peer step
+    unsigned int flag;         // this step's epoch
+    const uint4 *rho;          // local region [e&1][0]; rank r at + r * n_nodes
+    size_t n_nodes;
+    double dV;                 // rho = 1 - dV * (sum over ranks, in rank order)
+    double *rho_full;          // CPU-convention rho for later downloads
+    int *status;               // set to 1 if a word never arrived (bounded spin)
 };
 
 #ifdef __CUDACC__
@@ -136,63 +132,70 @@ struct PeerRecv // receiver side (tail_small_kernel / peer_gather_kernel)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// Receiver: thread r < world spins (bounded, ~17 s; not at all once a wait has already given up) until rank r's counter of this
-// parity has reached the epoch's target.  Call from all threads of the block and follow with __syncthreads(); read the slots
-// with __ldcg (L2: the peers wrote them behind L1's back).
-__device__ __forceinline__ void peer_wait_all(const PeerRecv &X)
+// ---- the wire encoding
+__device__ __forceinline__ void peer_store_double(uint4 *dst, double v, unsigned flag)
 {
-    if (static_cast<int>(threadIdx.x) < X.world) {
-        const unsigned long long *f = X.counters + threadIdx.x;
-        const long long t0 = clock64();
-        const bool gave_up_before = *reinterpret_cast<volatile int *>(X.status) != 0; // sticky: later steps do not wait again
+    const unsigned lo = static_cast<unsigned>(__double2loint(v)), hi = static_cast<unsigned>(__double2hiint(v));
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(flag), "r"(hi), "r"(flag) : "memory");
+}
+// four slot loads in flight at once (null pointer: 0.0): v[u] = *src[u], polled like peer_rank_sum's
+__device__ __forceinline__ void ll_load4(const uint4 *const (&src)[4], unsigned flag, int *status, double (&v)[4])
+{
+    unsigned a[4], fa[4], b[4], fb[4];
+    long long t0 = 0;
+    for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (src[u]) asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a[u]), "=r"(fa[u]), "=r"(b[u]), "=r"(fb[u]) : "l"(src[u]) : "memory");
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (src[u]) ok = ok && fa[u] == flag && fb[u] == flag;
+        if (ok) break;
+        if (t0 == 0) {
+            if (*reinterpret_cast<volatile int *>(status) != 0) break;
+            t0 = clock64();
+        } else if (clock64() - t0 > (1ll << 35)) {
+            *status = 1;
+            break;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = src[u] ? __hiloint2double(static_cast<int>(b[u]), static_cast<int>(a[u])) : 0.0;
+}
+// sum over the ranks, in rank order, of the word at `src + r * stride`: the loads poll (bounded, ~17 s; they give up at once after
+// an earlier give-up) until both halves of every value carry this step's epoch.  Volatile loads: served by L2, where the peers'
+// stores land.  Up to four ranks' loads are in flight at once.
+// `self` >= 0: that rank's value is `own` (no load).
+__device__ __forceinline__ double peer_rank_sum(const uint4 *src, size_t stride, int world, unsigned flag, int *status, int self, double own)
+{
+    double sum = 0;
+    for (int r0 = 0; r0 < world; r0 += 4) {
+        unsigned a[4], fa[4], b[4], fb[4];
+        long long t0 = 0;
         for (;;) {
-            unsigned long long v;
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-            if (v >= X.target || gave_up_before) break;
-            if (clock64() - t0 > (1ll << 35)) { // a peer never pushed: do not hang the GPU, report through the status word
-                *X.status = 1;
+            bool ok = true;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (r0 + u < world && r0 + u != self)
+                    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a[u]), "=r"(fa[u]), "=r"(b[u]), "=r"(fb[u]) : "l"(src + (r0 + u) * stride) : "memory");
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (r0 + u < world && r0 + u != self) ok = ok && fa[u] == flag && fb[u] == flag;
+            if (ok) break;
+            if (t0 == 0) {
+                if (*reinterpret_cast<volatile int *>(status) != 0) break;
+                t0 = clock64();
+            } else if (clock64() - t0 > (1ll << 35)) {
+                *status = 1;
                 break;
             }
         }
-    }
-}
-
-// One of the 8 strided partial sums of a node over the slots of ALL ranks: for w in 0..7, the slots of CTAs b_lo+w, b_lo+w+8, ...
-// of rank 0, then of rank 1, ... (loads four at a time; + 0.0 is exact, so the order is that of one-by-one addition).
-__device__ __forceinline__ double peer_slot_sum(const PeerRecv &X, unsigned long long l, int w)
-{
-    double sum = 0;
-    for (int r = 0; r < X.world; ++r) {
-        const PeerHeader H = X.headers[r];
-        if (H.n_tiles == 0 || l < H.l_first || l > H.l_last) continue;
-        const unsigned long long rel = l - H.l_first;
-        const unsigned tile = static_cast<unsigned>(rel / H.TN), lane = static_cast<unsigned>(rel % H.TN);
-        const unsigned b_lo = (tile * H.rpt) / H.rpc, b_hi = ((tile + 1) * H.rpt - 1) / H.rpc;
-        const double *slots = X.slots + static_cast<size_t>(r) * X.slot_cap;
-        for (unsigned b = b_lo + w; b <= b_hi; b += 32) {
-            double v[4];
 #pragma unroll
-            for (unsigned u = 0; u < 4; ++u) {
-                const unsigned bb = b + 8 * u;
-                v[u] = 0.0;
-                if (bb <= b_hi) {
-                    const unsigned t_first = (bb * H.rpc) / H.rpt;
-                    v[u] = __ldcg(slots + (static_cast<size_t>(bb) * H.Tmax + (tile - t_first)) * 32 + lane);
-                }
-            }
-            sum = (((sum + v[0]) + v[1]) + v[2]) + v[3];
-        }
+        for (int u = 0; u < 4; ++u)
+            if (r0 + u < world) sum += r0 + u == self ? own : __hiloint2double(static_cast<int>(b[u]), static_cast<int>(a[u]));
     }
     return sum;
-}
-
-// rho[l] = 1 - dV * (sum of the 8 partial sums, in order): identical on every GPU
-__device__ __forceinline__ double peer_rho(const PeerRecv &X, unsigned long long l)
-{
-    double tot = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) tot += peer_slot_sum(X, l, w);
-    return 1 - X.headers[0].dV * tot;
 }
 #endif
 
@@ -204,23 +207,19 @@ struct PeerState
     size_t xb_bytes = 0;
     unsigned char *peer_xb[kMaxPeers] = {};
     unsigned long long epoch = 0;
-    size_t slot_cap = 0;                // doubles per (parity, rank) slot region
     int *d_status = nullptr;
     PeerPush push{};                    // of the step being launched
     PeerRecv recv{};
 };
 
 // In-kernel epilogue of the backtrace kernel (rho mode).  mode 1: the last CTA to finish adds the slots of every tile in a fixed
-// order (what finish_rho_kernel does as a separate launch).  mode 3 (multi-GPU step): no reduction here at all -- every CTA has
-// stored its slots into every GPU's exchange buffer as it went and only signs off on the peers' counters (PeerPush).  mode 0:
-// none -- the fused tail reduces the slots itself.
+// order (what finish_rho_kernel does as a separate launch).  mode 0: none -- the fused tail (or finish_rho_kernel) adds the slots.
 struct EpilogueParams
 {
-    int mode;                 // 0 none, 1 finish (last-CTA slot reduction), 3 push every slot to the peers (multi-GPU step)
+    int mode;                 // 0 none, 1 finish (last-CTA slot reduction)
     unsigned int n_active;    // CTAs that take part (blockIdx.x < n_active)
     unsigned int *done;       // device counter, zero between launches
     FinishParams F;
-    PeerPush X;
 };
 
 struct Handle
@@ -240,6 +239,10 @@ struct Handle
     // rho / reduction
     double *d_rho_partial = nullptr, *d_rho_full = nullptr, *d_partials = nullptr;
     size_t partials_cap = 0; // doubles
+    uint4 *d_partials_ll = nullptr; // the same slots as self-validating words (fused steps on grids the one-CTA tail handles)
+    size_t partials_ll_cap = 0;
+    unsigned int slot_epoch = 0;    // epoch of the last launch that wrote d_partials_ll (never 0: the buffer starts zeroed)
+    int *d_ll_status = nullptr;     // set to 1 by a polling load that gave up
     double *d_metrics = nullptr, *d_mpartials = nullptr;
     double *d_energy = nullptr; // [Nt+1]
     double *d_stage = nullptr;  // device staging for one reference-format level
@@ -275,7 +278,7 @@ struct Handle
     unsigned int *d_done = nullptr; // arrival counter of the backtrace kernel's last-CTA epilogue
     unsigned long long vstride = 1, voff = 0; // velocity share of the next backtrace launch (multi-GPU step), else 1, 0
     PeerState px;
-    bool peer_push = false;      // the next backtrace launch pushes its slots into every GPU's exchange buffer (peer_step)
+    bool peer_push = false;      // the next backtrace launch is this GPU's share of a multi-GPU step: its sums go to every GPU (peer_step)
     int tn_force = 0;            // nodes per tile forced by nufi_b200_set_tile_nodes (0: automatic)
     bool mgrid_set = false;      // 1d: compute_metrics integrates over `mconf`'s (x,u) grid instead of the field grid's
     nufi_b200_config1d mconf{};
@@ -334,6 +337,7 @@ int launch_sample_f(Handle *h, size_t n, size_t npts, const double *d_pts, doubl
 int launch_sample_field(Handle *h, const double *d_ref_level, int der, size_t npts, const double *d_pts, double *d_out); // runs the pending slot reduction into d_rho_partial / d_rho_full
 // tail.cu
 int tail_init(Handle *h);
+bool tail_is_small(const Handle *h); // the fused one-CTA tail will run (grid small enough, or forced)
 void tail_destroy(Handle *h);
 // d_rho_full == nullptr: take rho from the pending slot reduction of the last backtrace launch
 // from_peer: rho = 1 + sum over ranks of the exchange buffer (h->px.recv), waited for inside the tail
@@ -343,7 +347,7 @@ void peer_free(Handle *h);
 int peer_alloc(Handle *h, int world);
 int peer_prepare_step(Handle *h);                 // next epoch: fills h->px.push / h->px.recv
 int launch_peer_gather(Handle *h);                // exchange buffer -> d_rho_full (large grids, cuFFT tail)
-int launch_peer_noop(Handle *h);                  // a rank without work still has to contribute its counter units
+int launch_peer_noop(Handle *h);                  // a rank without work still owes every GPU its (zero) sums of this epoch
 int tail_filter(Handle *h, const double *d_values, int mode); // 1: poisson solve, 2: interpolate; result in d_field
 int expand_field_to_stage(Handle *h);
 double *tail_energy_scratch(Handle *h);

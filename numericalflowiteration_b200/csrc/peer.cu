@@ -2,15 +2,18 @@
 //
 // Replaces the reference's fan-in (cuda_kernel::download_rho's blocking copy + host add per device, nufi/cuda_kernel.cu:135-145,
 // nufi/cuda_scheduler.hpp:113-118, and MPI_Allreduce on host buffers, bin/test_nufi_gpu_3d.cpp:158) -- and the NCCL all-reduce
-// this library used first -- by direct stores into peer memory:
-//   * the backtrace kernel (epilogue mode 3, backtrace_kernel.cuh): every CTA stores each per-(CTA, tile) slot it finishes into
-//     the exchange buffer of EVERY GPU (NVLink stores) and, when it is done, fences once and adds to a per-(rank, parity) counter
-//     on every GPU.  There is no reduction and no serial section in the kernel: it ends when its CTAs end;
-//   * the field tail (tail_small_kernel / peer_gather_kernel) acquires the `world` counters and adds the slots of all ranks in a
-//     fixed order, so all replicas compute bit-identical rho, phi and histories with no collective call, no extra launch for
-//     the reduction and no host synchronisation.  Two parities make the buffers safe to reuse: a rank can only write epoch e+2
-//     after its tail of e+1 saw every peer's push of e+1, which those peers issued after their tail of e had read epoch e.
-//     (r01: the kernel's LAST CTA reduced all tiles and pushed the reduced rho -- a serial epilogue of ~9 us on a 150 us step.)
+// this library used first -- by direct stores into peer memory (layout and wire encoding: internal.cuh):
+//   * the backtrace kernel (epilogue mode 3, backtrace_kernel.cuh): the last CTA to finish a tile adds the tile's per-(CTA, tile)
+//     slots in a fixed order and stores the 32 sums into the exchange buffer of EVERY GPU (NVLink stores), every 8-byte word
+//     carrying the step's epoch beside its 32 bits of payload.  Tiles are reduced and pushed in parallel by whichever CTAs finish
+//     them; no system-scope fence, no flag, no serial section: the kernel ends when its CTAs end;
+//   * the field tail (tail_small_kernel / peer_gather_kernel) adds the ranks' sums in rank order, polling every word it loads
+//     until it carries this step's epoch -- it does not even wait for its own GPU's backtrace grid to retire -- so all replicas
+//     compute bit-identical rho, phi and histories with no collective call, no extra launch and no host synchronisation.
+//     History of this exchange (profiles/r02_peer_exchange.md): r01 = the kernel's LAST CTA reduced all tiles serially and pushed
+//     the result behind a system-scope fence (3.8 us alone) and a flag, ~9 us on a 150 us step; r02 v2/v3 = every CTA pushed its
+//     raw slots and the one-CTA tail added world x (CTAs x tiles) of them -- no sender epilogue, but a tail that grew with the
+//     GPU count (33 us at 8 GPUs).
 // Mapping of the peers' buffers: one process driving all GPUs (nufi_b200_group_*) enables direct peer access; one process per
 // GPU (torchrun) exchanges cudaIpcMemHandle_t through the host layer (nufi_b200_peer_export / _attach).
 #include "internal.cuh"
@@ -23,19 +26,18 @@ namespace nufi_b200
 namespace
 {
 
-// exchange buffer -> d_rho_full for grids too large for the single-CTA tail (the cuFFT path reads rho from memory)
-__global__ void __launch_bounds__(256) peer_gather_kernel(const __grid_constant__ PeerRecv X, size_t n_nodes)
+// exchange buffer -> d_rho_full for grids too large for the single-CTA tail (the cuFFT path reads rho from memory).  No
+// pdl_wait: the words validate themselves, and nothing else the kernels ahead on the stream write is read here.
+__global__ void __launch_bounds__(256) peer_gather_kernel(const __grid_constant__ PeerRecv X)
 {
-    pdl_wait();
-    peer_wait_all(X);
-    __syncthreads();
-    for (size_t l = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; l < n_nodes; l += static_cast<size_t>(gridDim.x) * blockDim.x)
-        X.rho_full[l] = peer_rho(X, l);
+    pdl_trigger();
+    for (size_t l = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; l < X.n_nodes; l += static_cast<size_t>(gridDim.x) * blockDim.x)
+        X.rho_full[l] = 1 - X.dV * peer_rank_sum(X.rho + l, X.n_nodes, X.world, X.flag, X.status, -1, 0.0);
 }
 
-size_t slot_offset(const Handle *h, int parity, int rank)
+size_t region_offset(const Handle *h, int parity, int rank)
 {
-    return kPeerCounterBytes + kPeerHeaderBytes + (static_cast<size_t>(parity) * h->px.world + rank) * h->px.slot_cap * sizeof(double);
+    return (static_cast<size_t>(parity) * h->px.world + rank) * h->n_nodes * sizeof(uint4);
 }
 
 } // namespace
@@ -57,19 +59,16 @@ int peer_alloc(Handle *h, int world)
     peer_free(h);
     PeerState &px = h->px;
     px.world = world;
-    // slot space per (parity, rank): grid x Tmax x 32 doubles with Tmax = (rpc-1)/rpt + 2 <= n_tiles/grid + 3 (tiles of 32 nodes)
-    const size_t n_tiles = (h->n_nodes + 31) / 32;
-    px.slot_cap = static_cast<size_t>(h->sm_count) * (n_tiles / h->sm_count + 3) * 32;
-    px.xb_bytes = kPeerCounterBytes + kPeerHeaderBytes + 2 * static_cast<size_t>(world) * px.slot_cap * sizeof(double);
+    px.xb_bytes = 2 * static_cast<size_t>(world) * h->n_nodes * sizeof(uint4);
     NUFI_CUDA_CHECK(h, cudaMalloc(&px.xb, px.xb_bytes));
     NUFI_CUDA_CHECK(h, cudaMemset(px.xb, 0, px.xb_bytes));
     NUFI_CUDA_CHECK(h, cudaMalloc(&px.d_status, sizeof(int)));
     NUFI_CUDA_CHECK(h, cudaMemset(px.d_status, 0, sizeof(int)));
-    NUFI_CUDA_CHECK(h, cudaDeviceSynchronize()); // the zeroed counters are in place before any peer learns the address
+    NUFI_CUDA_CHECK(h, cudaDeviceSynchronize()); // the zeroed words (epoch 0 = "nothing yet") are in place before any peer learns the address
     return NUFI_B200_OK;
 }
 
-// Next epoch: pointers for the sender, counter target and slot regions for the receiver.
+// Next epoch: pointers and the epoch word for the sender, the local regions for the receiver.
 int peer_prepare_step(Handle *h)
 {
     PeerState &px = h->px;
@@ -78,18 +77,19 @@ int peer_prepare_step(Handle *h)
     const int parity = static_cast<int>(e & 1);
     PeerPush P{};
     P.world = px.world;
-    for (int p = 0; p < px.world; ++p) {
-        P.slots[p] = reinterpret_cast<double *>(px.peer_xb[p] + slot_offset(h, parity, px.rank));
-        P.counter[p] = reinterpret_cast<unsigned long long *>(px.peer_xb[p]) + parity * kMaxPeers + px.rank;
-        P.header[p] = reinterpret_cast<PeerHeader *>(px.peer_xb[p] + kPeerCounterBytes) + parity * kMaxPeers + px.rank;
-    }
+    P.rank = px.rank;
+    P.flag = static_cast<unsigned int>(e & 0xffffffffull);
+    if (P.flag == 0) P.flag = 0x80000000u; // never the value the zeroed buffers hold (after 2^32 steps)
+    for (int p = 0; p < px.world; ++p) P.rho[p] = reinterpret_cast<uint4 *>(px.peer_xb[p] + region_offset(h, parity, px.rank));
     PeerRecv R{};
     R.world = px.world;
-    R.counters = reinterpret_cast<const unsigned long long *>(px.xb) + parity * kMaxPeers;
-    R.target = ((e + (e & 1)) / 2) * kPeerUnit; // epochs of this parity so far, kPeerUnit from every rank in each
-    R.headers = reinterpret_cast<const PeerHeader *>(px.xb + kPeerCounterBytes) + parity * kMaxPeers;
-    R.slots = reinterpret_cast<const double *>(px.xb + slot_offset(h, parity, 0));
-    R.slot_cap = px.slot_cap;
+    R.flag = P.flag;
+    R.rho = reinterpret_cast<const uint4 *>(px.xb + region_offset(h, parity, 0));
+    R.n_nodes = h->n_nodes;
+    const nufi_b200_config3d &c = h->c; // rho.hpp:136-145, 291-307, 441-459: du recomputed from the bounds
+    R.dV = (c.u_max - c.u_min) / c.Nu;
+    if (h->dim >= 2) R.dV *= (c.v_max - c.v_min) / c.Nv;
+    if (h->dim >= 3) R.dV *= (c.w_max - c.w_min) / c.Nw;
     R.rho_full = h->d_rho_full;
     R.status = px.d_status;
     px.push = P;
@@ -101,7 +101,7 @@ int launch_peer_gather(Handle *h)
 {
     size_t blocks = (h->n_nodes + 255) / 256;
     if (blocks > 592) blocks = 592;
-    NUFI_CUDA_CHECK(h, launch_chained(h, peer_gather_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, h->px.recv, h->n_nodes));
+    NUFI_CUDA_CHECK(h, launch_chained(h, peer_gather_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, h->px.recv));
     h->launches += 1;
     return NUFI_B200_OK;
 }
@@ -185,7 +185,7 @@ int nufi_b200_peer_step(nufi_b200_handle *h, size_t n)
         hh->peer_push = true;
         hh->vstride = static_cast<unsigned long long>(px.world);
         hh->voff = static_cast<unsigned long long>(px.rank);
-        rc = nufi_b200_compute_rho(h, n, 0, hh->n_nodes * hh->n_vel); // backtrace whose CTAs push their slots to every GPU
+        rc = nufi_b200_compute_rho(h, n, 0, hh->n_nodes * hh->n_vel); // backtrace whose CTAs push the finished tiles to every GPU
         hh->peer_push = false;
         hh->vstride = 1;
         hh->voff = 0;
@@ -204,6 +204,9 @@ int nufi_b200_peer_status(nufi_b200_handle *h, int *timed_out)
     if (!hh->px.d_status) return NUFI_B200_OK;
     NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
     NUFI_CUDA_CHECK(hh, cudaMemcpy(timed_out, hh->px.d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    int slots = 0; // the tail's polling loads of this GPU's own slots
+    NUFI_CUDA_CHECK(hh, cudaMemcpy(&slots, hh->d_ll_status, sizeof(int), cudaMemcpyDeviceToHost));
+    *timed_out |= slots;
     return NUFI_B200_OK;
 }
 

@@ -286,7 +286,8 @@ struct SmallTailParams
     const double2 *twx, *twy, *twz; // (cos, sin)(2 pi m / N_d)
     const double *rho;              // CPU-convention rho on the device, or nullptr: reduce the backtrace slots (F)
     FinishParams F;
-    PeerRecv X;                     // X.world > 0: rho from the slots of all ranks in the peer exchange buffer (waits for the counters)
+    PeerRecv X;                     // X.world > 0 (multi-GPU step): rho = the per-node sums of ALL ranks, from the peer exchange buffer
+    PeerPush XP;                    // XP.world > 0: this rank's sums (from its slots, F) go to the peers first; 0: the words are all there
     double *level, *raw1d, *energy_out;
 };
 
@@ -446,10 +447,8 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
     // slot bookkeeping without integer divisions in the load loops: first tile of every backtrace CTA and the CTA range of every
     // tile, tabulated here (one division per thread, hidden behind the backtrace kernel by the programmatic launch)
     __shared__ unsigned short s_tfirst[256], s_blo[128], s_bhi[128];
-    // (multi-GPU step: S.F holds THIS rank's launch geometry; the peers' headers are compared with it once they have arrived)
-    const bool tabulated = !S.rho && S.F.n_tiles > 0 && S.F.n_tiles <= 128 && S.F.rpc > 0 && (S.F.rpt * S.F.n_tiles + S.F.rpc - 1) / S.F.rpc <= 256;
-    __shared__ int s_same_geometry;
-    if (threadIdx.x == 0) s_same_geometry = tabulated ? 1 : 0;
+    const bool from_slots = !S.rho && S.F.n_tiles > 0;
+    const bool tabulated = from_slots && S.F.n_tiles <= 128 && S.F.rpc > 0 && (S.F.rpt * S.F.n_tiles + S.F.rpc - 1) / S.F.rpc <= 256;
     if (tabulated) {
         const FinishParams &F = S.F;
         const unsigned n_ctas = (F.rpt * F.n_tiles + F.rpc - 1) / F.rpc;
@@ -460,102 +459,68 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
         }
     }
     TAIL_MARK(8);
-    pdl_wait(); // everything below reads what the kernels ahead of this one on the stream wrote
+    // Everything below reads what the kernels ahead of this one on the stream wrote -- unless all of it comes as self-validating
+    // words (slots of a fused step, the peers' sums of a multi-GPU step; internal.cuh): then the tail starts adding as soon as
+    // the words land instead of waiting for the backtrace grid to drain its stores and retire.  (Level n, rho and the energy
+    // slot written below are touched by no kernel still in flight.)
+    const bool polled = !S.rho && (!from_slots || S.F.slots_ll != nullptr);
+    if (!polled) pdl_wait();
     __syncthreads(); // the slot tables above are complete
     TAIL_MARK(9);
     // ---- rho (either given, or the fixed-order sum of the backtrace kernel's per-(CTA, tile) slots: per node 8 strided
     //      partial sums over the CTAs that touched its tile, then added in order -- the association of finish_rho_kernel)
     if (S.rho) {
         for (int l = threadIdx.x; l < N; l += blockDim.x) A[l] = make_double2(S.rho[l], 0.0);
-    } else if (S.X.world) { // multi-GPU step: the all-reduce happens here -- the slots of ALL ranks, pushed into this GPU's memory
-        peer_wait_all(S.X);
-        if (static_cast<int>(threadIdx.x) < S.X.world) { // do all ranks' launches have this rank's geometry?  (they do whenever the
-            // velocity nodes divide evenly over the ranks; then the tables above serve every rank's slots)
-            const unsigned int *hw = reinterpret_cast<const unsigned int *>(S.X.headers + threadIdx.x);
-            const unsigned long long *hl = reinterpret_cast<const unsigned long long *>(S.X.headers + threadIdx.x);
-            const FinishParams &F = S.F;
-            const bool same = __ldcg(hw + 0) == F.rpt && __ldcg(hw + 1) == F.rpc && __ldcg(hw + 2) == F.Tmax && __ldcg(hw + 3) == F.n_tiles &&
-                              __ldcg(hw + 4) == F.TN && __ldcg(hl + 4) == F.l_first && __ldcg(hl + 5) == F.l_last;
-            if (!same) s_same_geometry = 0;
+    } else if (!from_slots) { // multi-GPU step of a rank without a share of its own: every rank's sums are in the exchange buffer
+        for (int l = threadIdx.x; l < N; l += blockDim.x) {
+            const double r = 1 - S.X.dV * peer_rank_sum(S.X.rho + l, S.X.n_nodes, S.X.world, S.X.flag, S.X.status, -1, 0.0);
+            S.X.rho_full[l] = r;
+            A[l] = make_double2(r, 0.0);
         }
-        __syncthreads();
-        TAIL_MARK(10); // peer mode: [9 -> 10] = wait for the peers' counters, [10 -> 1] = slot reduction over all ranks
-        const double dV = S.F.dV;
-        const bool fast = s_same_geometry != 0;
-        const unsigned tn_log2 = 31 - __clz(S.F.TN);
-        // one of the 8 strided partial sums of node l over the slots of all ranks (rank 0's CTAs b_lo+w, b_lo+w+8, ..., then
-        // rank 1's, ...): table-driven when every rank shares this rank's geometry, else from each rank's own header
-        auto rank_sum = [&](int l, int w) {
-            if (!fast) return peer_slot_sum(S.X, l, w);
-            const FinishParams &F = S.F;
-            const unsigned tile = static_cast<unsigned>(l) >> tn_log2, lane = static_cast<unsigned>(l) & (F.TN - 1);
-            const unsigned b_lo = s_blo[tile], b_hi = s_bhi[tile];
-            double sum = 0;
-            for (int r = 0; r < S.X.world; ++r) {
-                const double *slots = S.X.slots + static_cast<size_t>(r) * S.X.slot_cap;
-                for (unsigned b = b_lo + w; b <= b_hi; b += 32) {
-                    double v[4];
-#pragma unroll
-                    for (unsigned u = 0; u < 4; ++u) {
-                        const unsigned bb = b + 8 * u;
-                        v[u] = bb <= b_hi ? __ldcg(slots + (static_cast<size_t>(bb) * F.Tmax + (tile - s_tfirst[bb])) * 32 + lane) : 0.0;
-                    }
-                    sum = (((sum + v[0]) + v[1]) + v[2]) + v[3]; // + 0.0 is exact: the order of one-by-one addition
-                }
-            }
-            return sum;
-        };
-        if (8 * N <= 2 * kSmallPart) { // the 8 partial sums of a node spread over up to 8 threads, combined in order afterwards
-            int G = 1;
-            while (2 * G * N <= static_cast<int>(blockDim.x) && G < 8) G *= 2;
-            double *ps = reinterpret_cast<double *>(part); // [8][N]
-            for (int it = threadIdx.x; it < N * G; it += blockDim.x) {
-                int l = it, g = 0;
-                while (l >= N) { l -= N; ++g; }
-                for (int w = g; w < 8; w += G) ps[w * N + l] = rank_sum(l, w);
-            }
-            __syncthreads();
-            for (int l = threadIdx.x; l < N; l += blockDim.x) {
-                double tot = 0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) tot += ps[w * N + l];
-                const double r = 1 - dV * tot;
-                S.X.rho_full[l] = r;
-                A[l] = make_double2(r, 0.0);
-            }
-        } else {
-            for (int l = threadIdx.x; l < N; l += blockDim.x) {
-                double tot = 0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) tot += rank_sum(l, w);
-                const double r = 1 - dV * tot;
-                S.X.rho_full[l] = r;
-                A[l] = make_double2(r, 0.0);
-            }
-        }
+        TAIL_MARK(10);
     } else {
         const FinishParams &F = S.F;
         auto slot_sum = [&](unsigned tile, unsigned lane, unsigned b_lo, unsigned b_hi, int w) {
             double sum = 0;
             for (unsigned b = b_lo + w; b <= b_hi; b += 32) { // four loads in flight per trip; + 0.0 is exact, the order is kept
                 double v[4];
+                size_t at[4]; // slot index, or ~0: beyond the tile's last CTA
 #pragma unroll
                 for (unsigned u = 0; u < 4; ++u) {
                     const unsigned bb = b + 8 * u;
+                    at[u] = ~static_cast<size_t>(0);
                     if (bb <= b_hi) {
                         const unsigned t_first = tabulated ? s_tfirst[bb] : (bb * F.rpc) / F.rpt;
-                        v[u] = F.slots[(static_cast<size_t>(bb) * F.Tmax + (tile - t_first)) * 32 + lane];
-                    } else {
-                        v[u] = 0.0;
+                        at[u] = (static_cast<size_t>(bb) * F.Tmax + (tile - t_first)) * 32 + lane;
                     }
+                }
+                if (F.slots_ll) { // self-validating slots: poll until they carry this launch's epoch
+                    const uint4 *src[4];
+#pragma unroll
+                    for (unsigned u = 0; u < 4; ++u) src[u] = at[u] != ~static_cast<size_t>(0) ? F.slots_ll + at[u] : nullptr;
+                    ll_load4(src, F.slot_flag, F.status, v);
+                } else {
+#pragma unroll
+                    for (unsigned u = 0; u < 4; ++u) v[u] = at[u] != ~static_cast<size_t>(0) ? F.slots[at[u]] : 0.0;
                 }
                 sum = (((sum + v[0]) + v[1]) + v[2]) + v[3];
             }
             return sum;
         };
         auto store_rho = [&](int l, double tot) {
-            const double r = 1 - F.dV * tot;
             F.rho_partial[l] = -F.dV * tot;
+            if (S.X.world) { // multi-GPU step: the all-reduce happens here.  This rank's sum goes straight into the other GPUs'
+                // exchange buffers (NVLink stores); then all ranks' sums are added in rank order (own from the register, the
+                // others polled until they carry this step's epoch) -- the same association, hence the same bits, on every GPU
+                for (int p = 0; p < S.XP.world; ++p)
+                    if (p != S.XP.rank) peer_store_double(S.XP.rho[p] + l, tot, S.XP.flag);
+                tot = peer_rank_sum(S.X.rho + l, S.X.n_nodes, S.X.world, S.X.flag, S.X.status, S.XP.rank, tot);
+                const double r = 1 - S.X.dV * tot;
+                S.X.rho_full[l] = r;
+                A[l] = make_double2(r, 0.0);
+                return;
+            }
+            const double r = 1 - F.dV * tot;
             if (F.rho_full) F.rho_full[l] = r;
             A[l] = make_double2(r, 0.0);
         };
@@ -674,7 +639,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
 #ifdef NUFI_TAIL_TIMING
     TAIL_MARK(5);
     if (threadIdx.x == 0)
-        printf("tail phases (cycles): rho+tw %lld [tables %lld, pdl_wait %lld, slot loads %lld, combine %lld]  fwd %lld  symbol %lld  inv %lld  expand %lld  total %lld\n",
+        printf("tail phases (cycles): rho+tw %lld [tables %lld, pdl_wait %lld, slot loads (peer step: polling loads of all ranks' sums) %lld, combine %lld]  fwd %lld  symbol %lld  inv %lld  expand %lld  total %lld\n",
                tmark[1] - tmark[0], tmark[8] - tmark[0], tmark[9] - tmark[8], tmark[10] - tmark[9], tmark[1] - tmark[10],
                tmark[2] - tmark[1], tmark[3] - tmark[2], tmark[4] - tmark[3], tmark[5] - tmark[4], tmark[5] - tmark[0]);
 #endif
@@ -809,6 +774,8 @@ static bool small_tail_ok(const Handle *h)
            h->c.Nz <= kSmallMaxDim;
 }
 
+bool tail_is_small(const Handle *h) { return small_tail_ok(h) && h->tail_force != 1; }
+
 // rho (CPU convention, device) -> level n in the device history + energy[n].
 // d_rho_full == nullptr: rho comes from the pending slot reduction of the last backtrace launch (fused step).
 int tail_run(Handle *h, size_t n, const double *d_rho_full, bool from_peer)
@@ -840,22 +807,24 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full, bool from_peer)
         S.level = level;
         S.raw1d = h->d_raw ? h->d_raw + n * h->raw_stride : nullptr;
         S.energy_out = h->d_energy + n;
-        if (from_peer) {
+        if (from_peer) { // multi-GPU step: this rank's slots (if it had a share) -> its sums -> every GPU; rho from all ranks' sums
             S.rho = nullptr;
             S.X = h->px.recv;
-            const PeerHeader &H = h->px.push.hdr; // this rank's launch geometry (n_tiles = 0: this rank had no work)
-            S.F.rpt = H.rpt; S.F.rpc = H.rpc; S.F.Tmax = H.Tmax; S.F.n_tiles = H.n_tiles; S.F.TN = H.TN ? H.TN : 32;
-            S.F.l_first = H.l_first; S.F.l_last = H.l_last;
-            S.F.dV = H.n_tiles ? H.dV : h->dim == 1 ? (c.u_max - c.u_min) / c.Nu
-                                 : (h->dim == 2 ? (c.u_max - c.u_min) / c.Nu * ((c.v_max - c.v_min) / c.Nv)
-                                                : (c.u_max - c.u_min) / c.Nu * ((c.v_max - c.v_min) / c.Nv) * ((c.w_max - c.w_min) / c.Nw));
+            if (h->fin_pending) {
+                S.F = h->fin;
+                S.XP = h->px.push;
+                h->fin_pending = false;
+            }
         } else if (d_rho_full) {
             S.rho = d_rho_full;
-        } else {
-            if (!h->fin_pending) return fail(h, NUFI_B200_ERR_ARG, "field tail: no rho on the device");
+        } else if (h->fin_pending && h->fin.slots_ll) { // fused step: the tail adds the slots itself
             S.rho = nullptr;
             S.F = h->fin;
             h->fin_pending = false;
+        } else { // the backtrace kernel's own epilogue, or finish_rho_kernel, leaves rho in memory
+            int rc = launch_finish(h);
+            if (rc) return rc;
+            S.rho = h->d_rho_full;
         }
         const size_t smem = (2 * h->n_nodes + 2 * (c.Nx + c.Ny + c.Nz) + kSmallPart) * sizeof(double2) + ((c.Nx + c.Ny + c.Nz + 1) & ~size_t(1)) * sizeof(double);
         if (smem > 48 * 1024)

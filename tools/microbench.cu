@@ -64,6 +64,53 @@ template <int WIDTH, int STRIDE> __global__ void lds_tp(double *out, long long *
     if (threadIdx.x == 0) cycles[0] = t1 - t0;
 }
 
+
+// FP64 issue throughput of one SM against the number of DISTINCT register operands per DFMA (register-file read bandwidth:
+// can the pipe sustain one warp-DFMA per 2 cycles per SMSP when none of its three 64-bit operands comes from the operand-reuse
+// cache?), and with 64-bit shared-memory loads mixed in.  MODE 0: x = fma(x, a, b) (two loop-invariant operands, the shape of
+// the roofline's peak loop); 1: x_i = fma(y_i, c, x_i) (one shared); 2: x_i = fma(y_i, z_i, x_i) (three distinct, the shape of
+// a spline contraction); 3: MODE 2 plus one LDS.64 per 4 DFMA (the 3d step's mix).
+template <int MODE> __global__ void dfma_tp(double *out, long long *cycles, int iters, double a, double b)
+{
+    __shared__ double sm[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) sm[i] = 1e-9 * i;
+    __syncthreads();
+    double x[8], y[8], z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x[i] = a * (i + 1) + threadIdx.x * 1e-6; y[i] = b + i * 1e-3 + threadIdx.x * 1e-9; z[i] = a - i * 1e-3 - threadIdx.x * 1e-9; }
+    int k = threadIdx.x & 1023;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (MODE == 0) x[i] = fma(x[i], a, b);
+                if (MODE == 1) x[i] = fma(y[i], a, x[i]);
+                if (MODE >= 2) x[i] = fma(y[i], z[i], x[i]);
+            }
+            if (MODE == 3) { y[u] += sm[k]; y[u + 4] += sm[k + 32]; k = (k + 64) & 1023; }
+        }
+    }
+    const long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i] + y[i] + z[i];
+    out[threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+template <int MODE> void run_dfma(const char *name, double *d_out, long long *d_cyc, int warps)
+{
+    const int iters = 2000;
+    dfma_tp<MODE><<<1, warps * 32>>>(d_out, d_cyc, iters, 0.999, 1e-3);
+    dfma_tp<MODE><<<1, warps * 32>>>(d_out, d_cyc, iters, 0.999, 1e-3);
+    long long c = 0;
+    cudaMemcpy(&c, d_cyc, sizeof(c), cudaMemcpyDeviceToHost);
+    const double dfma_per_smsp = double(iters) * 32 * warps / 4;
+    printf("%-52s %2d warps: %5.2f cycles per warp-DFMA per SMSP (pipe: 2.00)\n", name, warps, c / dfma_per_smsp);
+}
+
 template <int WIDTH, int STRIDE> void run_tp(const char *name, double *d_out, long long *d_cyc, int warps)
 {
     const int iters = 2000;
@@ -102,6 +149,12 @@ int main()
     run<7>("DFMA,DFMA (Horner)", d_out, d_cyc, 0.999, 2);
     double *d_big;
     cudaMalloc(&d_big, 1024 * sizeof(double));
+    for (int w : {4, 8, 16}) {
+        run_dfma<0>("DFMA x=fma(x,a,b): 1 varying operand", d_big, d_cyc, w);
+        run_dfma<1>("DFMA x_i=fma(y_i,a,x_i): 2 varying operands", d_big, d_cyc, w);
+        run_dfma<2>("DFMA x_i=fma(y_i,z_i,x_i): 3 varying operands", d_big, d_cyc, w);
+        run_dfma<3>("  ... + 2 LDS.64 per 8 DFMA", d_big, d_cyc, w);
+    }
     for (int w : {4, 8, 16, 32}) {
         run_tp<4, 1>("LDS.32 dense", d_big, d_cyc, w);
         run_tp<8, 1>("LDS.64 dense", d_big, d_cyc, w);
