@@ -145,43 +145,55 @@ __global__ void sample_field_kernel(const __grid_constant__ FieldSampleParams S)
 }
 
 template <int DIM, int ILP, bool STAGED, bool POW2, bool XPP>
-cudaError_t launch_variant(const BtParams &P, const EpilogueParams &E, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
+cudaError_t launch_variant(const BtParams &P, const EpilogueParams &E, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st, bool pdl)
 {
     auto kern = backtrace_kernel<DIM, ILP, STAGED, POW2, XPP>;
     if (smem_bytes > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
         if (e != cudaSuccess) return e;
     }
-    kern<<<grid, threads, smem_bytes, st>>>(P, E);
-    return cudaGetLastError();
+    // Programmatic dependent launch: the grid may become resident (barrier set-up, index arithmetic) while the kernel ahead of it
+    // on the stream -- in a run of fused steps the previous step's one-CTA field tail -- is still running; the kernel executes
+    // griddepcontrol.wait before it reads anything from global memory.
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, P, E);
 }
 
 template <int DIM, int ILP, bool XPP>
-cudaError_t launch_fmt(const BtParams &P, const EpilogueParams &E, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
+cudaError_t launch_fmt(const BtParams &P, const EpilogueParams &E, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st, bool pdl)
 {
     if (staged) {
-        return pow2 ? launch_variant<DIM, ILP, true, true, XPP>(P, E, grid, threads, smem_bytes, st)
-                    : launch_variant<DIM, ILP, true, false, XPP>(P, E, grid, threads, smem_bytes, st);
+        return pow2 ? launch_variant<DIM, ILP, true, true, XPP>(P, E, grid, threads, smem_bytes, st, pdl)
+                    : launch_variant<DIM, ILP, true, false, XPP>(P, E, grid, threads, smem_bytes, st, pdl);
     }
-    return pow2 ? launch_variant<DIM, ILP, false, true, XPP>(P, E, grid, threads, smem_bytes, st)
-                : launch_variant<DIM, ILP, false, false, XPP>(P, E, grid, threads, smem_bytes, st);
+    return pow2 ? launch_variant<DIM, ILP, false, true, XPP>(P, E, grid, threads, smem_bytes, st, pdl)
+                : launch_variant<DIM, ILP, false, false, XPP>(P, E, grid, threads, smem_bytes, st, pdl);
 }
 
 template <int DIM, int ILP>
-cudaError_t launch_ilp(const BtParams &P, const EpilogueParams &E, bool xpp, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st)
+cudaError_t launch_ilp(const BtParams &P, const EpilogueParams &E, bool xpp, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes, cudaStream_t st, bool pdl)
 {
     if constexpr (DIM >= 2) {
-        if (xpp) return launch_fmt<DIM, ILP, true>(P, E, staged, pow2, grid, threads, smem_bytes, st);
+        if (xpp) return launch_fmt<DIM, ILP, true>(P, E, staged, pow2, grid, threads, smem_bytes, st, pdl);
     }
-    return launch_fmt<DIM, ILP, false>(P, E, staged, pow2, grid, threads, smem_bytes, st);
+    return launch_fmt<DIM, ILP, false>(P, E, staged, pow2, grid, threads, smem_bytes, st, pdl);
 }
 
 template <int DIM>
 cudaError_t launch_dim(const BtParams &P, const EpilogueParams &E, int ilp, bool xpp, bool staged, bool pow2, unsigned grid, unsigned threads, size_t smem_bytes,
-                       cudaStream_t st)
+                       cudaStream_t st, bool pdl)
 {
-    return ilp == 2 ? launch_ilp<DIM, 2>(P, E, xpp, staged, pow2, grid, threads, smem_bytes, st)
-                    : launch_ilp<DIM, 1>(P, E, xpp, staged, pow2, grid, threads, smem_bytes, st);
+    return ilp == 2 ? launch_ilp<DIM, 2>(P, E, xpp, staged, pow2, grid, threads, smem_bytes, st, pdl)
+                    : launch_ilp<DIM, 1>(P, E, xpp, staged, pow2, grid, threads, smem_bytes, st, pdl);
 }
 
 int max_threads_for(int dim, int ilp, bool xpp)
@@ -425,9 +437,9 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     }
     cudaError_t e;
     if (h->order != 4) e = launch_backtrace_generic(h->order, h->dim, P, E, grid, threads, smem_bytes, h->stream);
-    else if (h->dim == 1) e = launch_dim<1>(P, E, ilp, false, staged, pow2, grid, threads, smem_bytes, h->stream);
-    else if (h->dim == 2) e = launch_dim<2>(P, E, ilp, h->xpp, staged, pow2, grid, threads, smem_bytes, h->stream);
-    else e = launch_dim<3>(P, E, ilp, h->xpp, staged, pow2, grid, threads, smem_bytes, h->stream);
+    else if (h->dim == 1) e = launch_dim<1>(P, E, ilp, false, staged, pow2, grid, threads, smem_bytes, h->stream, h->pdl);
+    else if (h->dim == 2) e = launch_dim<2>(P, E, ilp, h->xpp, staged, pow2, grid, threads, smem_bytes, h->stream, h->pdl);
+    else e = launch_dim<3>(P, E, ilp, h->xpp, staged, pow2, grid, threads, smem_bytes, h->stream, h->pdl);
     NUFI_CUDA_CHECK(h, e);
     if (h->kernel_timing) {
         NUFI_CUDA_CHECK(h, cudaEventRecord(ev_stop, h->stream));

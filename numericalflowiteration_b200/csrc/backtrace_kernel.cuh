@@ -555,6 +555,10 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
         __syncthreads();
     }
 
+    // Launched programmatically behind the kernel ahead on the stream (in a run of fused steps: the previous step's field tail,
+    // which is still writing the newest level): everything above ran beside it; nothing below may start before it has finished.
+    pdl_wait();
+
     if (STAGED && warp == W) {
         // ------------------------------------------------ producer warp: stream chunks newest -> oldest, once per round
         if (lane == 0) {
