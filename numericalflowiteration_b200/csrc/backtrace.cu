@@ -160,11 +160,22 @@ cudaError_t launch_variant(const BtParams &P, const EpilogueParams &E, unsigned 
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    unsigned na = 0;
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (P.cluster == 2) { // CTAs 2k, 2k+1 on neighbouring SMs: every history chunk is fetched once per pair (multicast)
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kern, P, E);
 }
 
@@ -213,6 +224,35 @@ int env_int(const char *name, int dflt)
 {
     const char *v = std::getenv(name);
     return v && *v ? std::atoi(v) : dflt;
+}
+
+// How many CTAs of a one-CTA-per-SM grid can be resident as clusters of two (pairs need two SMs of one GPC): asked once per
+// handle with a representative staged kernel at full shared-memory size; 0 = clusters cannot be used.
+int query_pair_ctas(const Handle *h)
+{
+    auto kern = backtrace_kernel<1, 2, true, true, false>;
+    const size_t smem = h->smem_optin > 2048 ? h->smem_optin - 1024 : 0;
+    if (smem == 0 || cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(h->sm_count & ~1));
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return 2 * n;
 }
 
 // chains (warps x points per thread) per SM beyond which a CTA-round's time grows with its width
@@ -296,7 +336,20 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     if (h->variant_force == 2 && 2ull * P.level_bytes > ring_budget)
         return fail(h, NUFI_B200_ERR_ARG, "staged variant forced but two levels do not fit in shared memory");
     const bool pow2 = is_pow2(c.Nx) && is_pow2(c.Ny) && is_pow2(c.Nz);
-    const unsigned grid = static_cast<unsigned>(h->sm_count);
+    // Staged variant, optional (NUFI_B200_CLUSTER=2): the persistent grid runs as clusters of two CTAs that share every history
+    // chunk (each fetches half, multicast to both), provided (nearly) all SMs can be paired.  Built to halve the L2 -> SM traffic
+    // of the fill (every SM streams the same levels); measured on B200 it changes nothing -- C1 0.1023 / 0.1023 ms, C2 0.1472 /
+    // 0.1491, C3 7.83 / 7.88, C4 0.238 / 0.237, C5-16 8.75 / 8.77 (off / on; profiles/r02_fill_path.md): the L2 already
+    // de-duplicates concurrent requests of neighbouring SMs for one line, the fill is bounded by what ONE SM can take in -- so
+    // it stays off by default and remains selectable (the parity suite runs it).
+    const bool want_pairs = staged && env_int("NUFI_B200_CLUSTER", 1) == 2;
+    if (want_pairs && h->pair_ctas == 0) {
+        h->pair_ctas = query_pair_ctas(h);
+        if (h->pair_ctas <= 0) h->pair_ctas = -1;
+    }
+    const bool paired = want_pairs && h->pair_ctas >= h->sm_count - 4 && h->pair_ctas >= 2;
+    const unsigned grid = paired ? static_cast<unsigned>(std::min(h->pair_ctas, h->sm_count & ~1)) : static_cast<unsigned>(h->sm_count);
+    P.cluster = paired ? 2 : 1;
 
     // ---- chunking of the staged history
     P.Lc = 1; P.stages = 0; P.stage_bytes = P.level_bytes;
@@ -451,7 +504,7 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
     if (P.TN != 32) std::snprintf(tn, sizeof(tn), "/tn%u", P.TN);
     char ord[16] = "";
     if (h->order != 4) std::snprintf(ord, sizeof(ord), "/order%d", h->order);
-    if (staged) std::snprintf(h->variant_buf, sizeof(h->variant_buf), "smem-tma%s/ilp%d/W%u/Lc%dx%d%s", fmt, ilp, P.W, P.Lc, P.stages, tn);
+    if (staged) std::snprintf(h->variant_buf, sizeof(h->variant_buf), "smem-tma%s%s/ilp%d/W%u/Lc%dx%d%s", paired ? "-mc2" : "", fmt, ilp, P.W, P.Lc, P.stages, tn);
     else std::snprintf(h->variant_buf, sizeof(h->variant_buf), "global%s%s/ilp%d/W%u%s", fmt, ord, ilp, P.W, tn);
     h->last_variant = h->variant_buf;
 

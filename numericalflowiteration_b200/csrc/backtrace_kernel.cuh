@@ -489,11 +489,52 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// ---- thread-block cluster of two CTAs sharing one stream of the history (BtParams::cluster == 2): every chunk is fetched from L2
+// ONCE per pair -- each CTA issues half of it as a multicast bulk copy that lands at the same shared-memory offset in both CTAs
+// and counts on both CTAs' `full` barriers -- half the L2 reads per SM.  Opt-in (NUFI_B200_CLUSTER=2): measured, it buys
+// nothing on B200 (profiles/r02_fill_path.md).
+__device__ __forceinline__ unsigned cluster_ctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() // every thread of every CTA of the cluster
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(unsigned long long *bar, unsigned rank)
+{
+    asm volatile("{ .reg .b32 ra; mapa.shared::cluster.u32 ra, %0, %1; mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra]; }" ::"r"(smem_u32(bar)), "r"(rank)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long *bar, unsigned parity) // acquires what a peer CTA released
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> the same shared-memory offset of every CTA in `mask`, completion counted on each one's mbarrier
+__device__ __forceinline__ void bulk_g2s_multicast(void *dst, const void *src, unsigned bytes, unsigned long long *bar, unsigned short mask)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
 // named barrier over the consumer warps only (the producer warp never joins)
 __device__ __forceinline__ void consumer_sync(unsigned threads) { asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); }
 
 constexpr int kMaxStages = 8;
-constexpr unsigned kBarBytes = 2 * kMaxStages * 8; // full[8], empty[8]
+constexpr unsigned kBarBytes = 3 * kMaxStages * 8; // full[8], empty[8], peer_free[8] (cluster pairs)
 constexpr unsigned kRedBytes = 32 * 32 * 8;        // consumer-warp reduction scratch [32 warps][32 lanes]
 constexpr unsigned kSmemFixed = kBarBytes + kRedBytes;
 
@@ -526,16 +567,23 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);
     unsigned long long *empty = full + kMaxStages;
+    unsigned long long *peer_free = empty + kMaxStages; // cluster pairs: "the other CTA's stage s may be overwritten"
     double(*sred)[32] = reinterpret_cast<double(*)[32]>(smem + kBarBytes);
     const unsigned char *ring = smem + kSmemFixed;
 
     const int lane = threadIdx.x & 31;
     const unsigned warp = threadIdx.x >> 5;
     const unsigned W = P.W;
+    const bool paired = STAGED && P.cluster == 2; // CTAs 2k, 2k+1 share the history stream (multicast)
     // this CTA's run of CTA-rounds
     const unsigned g0 = blockIdx.x * P.rpc;
-    if (g0 >= P.R) return; // whole CTA idle (uniform)
-    const unsigned my_rounds = min(P.rpc, P.R - g0);
+    const unsigned my_rounds = g0 < P.R ? min(P.rpc, P.R - g0) : 0;
+    unsigned pair_rounds = my_rounds; // a pair walks the ring in lockstep: the CTA with fewer rounds idles through the rest
+    if (paired) {
+        const unsigned g0p = (blockIdx.x ^ 1u) * P.rpc;
+        pair_rounds = max(my_rounds, g0p < P.R ? min(P.rpc, P.R - g0p) : 0u);
+    }
+    if (!paired && my_rounds == 0) return; // whole CTA idle (uniform)
     const unsigned t_first = g0 / P.rpt;
     // Chunks of the history, newest first, aligned at the TOP: chunk i holds levels [first_level - (i+1) Lc + 1, first_level - i Lc],
     // so every chunk but the last (which ends at level 0) has exactly Lc levels and the per-chunk code has no ragged cases.
@@ -549,10 +597,15 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
             for (int s = 0; s < P.stages; ++s) {
                 mbar_init(&full[s], 1);
                 mbar_init(&empty[s], W);
+                mbar_init(&peer_free[s], 1);
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
+        if (paired) {
+            cluster_sync_all(); // the partner's barriers exist before anything is sent to them
+            if (pair_rounds == 0) return;
+        }
     }
 
     // Launched programmatically behind the kernel ahead on the stream (in a run of fused steps: the previous step's field tail,
@@ -565,9 +618,16 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
             int s = 0;
             unsigned ph = 0;
             bool primed = false;
-            for (unsigned r = 0; r < my_rounds; ++r)
+            const unsigned crank = paired ? cluster_ctarank() : 0;
+            for (unsigned r = 0; r < pair_rounds; ++r)
                 for (int ci = 0; ci < n_chunks; ++ci) {
-                    if (primed) mbar_wait(&empty[s], ph ^ 1u);
+                    if (primed) {
+                        mbar_wait(&empty[s], ph ^ 1u);
+                        if (paired) { // both CTAs of the pair must be done with stage s before either half lands in both
+                            mbar_arrive_remote(&peer_free[s], crank ^ 1u);
+                            mbar_wait_cluster(&peer_free[s], ph ^ 1u);
+                        }
+                    }
                     const bool bottom = ci == n_chunks - 1;
                     const int cnt = bottom ? rem_levels : P.Lc;
                     const int lv_lo = bottom ? 0 : P.first_level - (ci + 1) * P.Lc + 1;
@@ -575,8 +635,15 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
                     mbar_expect_tx(&full[s], bytes);
                     const unsigned char *src = reinterpret_cast<const unsigned char *>(P.hist) + static_cast<size_t>(lv_lo) * P.level_bytes;
                     unsigned char *dst = const_cast<unsigned char *>(ring) + static_cast<size_t>(s) * P.stage_bytes;
-                    for (unsigned off = 0; off < bytes; off += 32768u)
-                        bulk_g2s(dst + off, src + off, min(32768u, bytes - off), &full[s]);
+                    if (paired) { // this CTA's half of the chunk, to both CTAs
+                        const unsigned half = (bytes / 2u) & ~15u;
+                        const unsigned lo = crank == 0 ? 0u : half, hi = crank == 0 ? half : bytes;
+                        for (unsigned off = lo; off < hi; off += 32768u)
+                            bulk_g2s_multicast(dst + off, src + off, min(32768u, hi - off), &full[s], static_cast<unsigned short>(3));
+                    } else {
+                        for (unsigned off = 0; off < bytes; off += 32768u)
+                            bulk_g2s(dst + off, src + off, min(32768u, bytes - off), &full[s]);
+                    }
                     if (++s == P.stages) { s = 0; ph ^= 1u; primed = true; }
                 }
         }
@@ -612,7 +679,21 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
         acc_lo = 0;
     };
 
-    for (unsigned r = 0; r < my_rounds; ++r) {
+    auto idle_round = [&]() { // no work for this warp in this round: keep the stage protocol going
+        if constexpr (STAGED) {
+            for (int ci = 0; ci < n_chunks; ++ci) {
+                mbar_wait(&full[s], ph);
+                if (lane == 0) mbar_arrive(&empty[s]);
+                if (++s == P.stages) { s = 0; ph ^= 1u; }
+            }
+        }
+    };
+
+    for (unsigned r = 0; r < pair_rounds; ++r) {
+        if (r >= my_rounds) { // the partner CTA of a pair still has rounds to go
+            idle_round();
+            continue;
+        }
         const unsigned g = g0 + r;
         const unsigned tile = g / P.rpt;
         const unsigned jr = g - tile * P.rpt;
@@ -623,14 +704,8 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
         // warp-unit of this warp: interleaved (default) = the warps of a round and the points of a thread are spread evenly
         // over the velocity range, so every CTA sees the same mix of fast/trapped orbits (equal bank-conflict load)
         const unsigned jc = P.interleave ? jr + warp * P.rpt : jr * W + warp;
-        if (jc >= P.upt) { // no unit for this warp in this round: keep the stage protocol going
-            if constexpr (STAGED) {
-                for (int ci = 0; ci < n_chunks; ++ci) {
-                    mbar_wait(&full[s], ph);
-                    if (lane == 0) mbar_arrive(&empty[s]);
-                    if (++s == P.stages) { s = 0; ph ^= 1u; }
-                }
-            }
+        if (jc >= P.upt) { // no unit for this warp in this round
+            idle_round();
             continue;
         }
 
@@ -770,6 +845,7 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
         }
     }
 
+    if (my_rounds == 0) return; // idle half of a pair: no slots, no part in the epilogue
     if (!P.metrics) {
         flush_tile(cur_tile);
         if (E.mode) { // ---- epilogue: the last CTA to arrive reduces the slots of all tiles

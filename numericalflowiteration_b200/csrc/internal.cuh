@@ -58,6 +58,7 @@ struct BtParams
     // staged variant: shared-memory ring of `stages` stages, each a chunk of Lc consecutive levels
     int Lc, stages;
     unsigned int stage_bytes;
+    int cluster;                     // 2: CTAs 2k, 2k+1 form a thread-block cluster and share every chunk (multicast halves); else 1
 };
 
 // sampling kernels (sample_f_kernel): f / ftilda / the flow map at arbitrary phase-space points
@@ -274,6 +275,7 @@ struct Handle
     bool kernel_timing = false;  // bracket every backtrace launch with a CUDA event pair (nufi_b200_set_kernel_timing)
     bool pdl = true;             // programmatic dependent launch of finish / tail behind the backtrace kernel (NUFI_B200_PDL=0: off)
     int sm_count = 148;
+    int pair_ctas = 0;           // CTAs of the persistent grid that can be resident as 2-CTA clusters (0: clusters unavailable)
     size_t smem_optin = 0;
     unsigned int *d_done = nullptr; // arrival counter of the backtrace kernel's last-CTA epilogue
     unsigned long long vstride = 1, voff = 0; // velocity share of the next backtrace launch (multi-GPU step), else 1, 0

@@ -47,6 +47,39 @@ def test_rho_teacher_forced(name, variant, xpp, histories, oracle, monkeypatch):
             assert err <= RHO_TOL, (name, variant, n, err, s.last_variant)
 
 
+@pytest.mark.parametrize("name", list(CASES))
+def test_cluster_pairs_share_the_history_stream(name, histories, oracle, monkeypatch):
+    """NUFI_B200_CLUSTER=2: the staged kernel runs as clusters of two CTAs, each fetching half of every history chunk and
+    multicasting it to both (opt-in).  Same rho as the unpaired kernel bit for bit (the arithmetic and the
+    order of every sum are unchanged), ragged cases included: a CTA whose partner has more rounds, an idle partner, and the
+    fused step reading the self-validating slots of a paired launch."""
+    conf, f0, coeffs, _ = histories[name]
+    with CudaScheduler(conf, f0) as s:
+        s.set_variant(2)
+        s.upload_history(coeffs, conf.Nt)
+        n = conf.Nt - 1
+        ref = s.eval_rho(n)
+        ref_variant = s.last_variant
+        monkeypatch.setenv("NUFI_B200_CLUSTER", "2")
+        got = s.eval_rho(n)
+        if "-mc2" not in s.last_variant:
+            pytest.skip(f"cluster pairs unavailable on this device ({s.last_variant})")
+        assert "-mc2" not in ref_variant
+        assert np.array_equal(got, ref), (name, s.last_variant)
+        assert rel_linf(got, oracle.rho(conf, f0, n, coeffs)) <= RHO_TOL
+        nq = n_quad(conf)
+        s.compute_rho(n, nq // 3, nq // 3 + max(1, nq // 50))  # a few tiles only: most pairs idle, some half idle
+        part = np.zeros(s.n_nodes)
+        s.download_rho(part)
+        want = oracle.rho_partial(conf, f0, n, coeffs, nq // 3, nq // 3 + max(1, nq // 50))
+        assert np.max(np.abs(part - want)) <= 1e-12 * max(np.max(np.abs(want)), 1e-300) + 1e-15
+        s.step(n)  # fused step on the paired kernel
+        lvl_pair = s.download_phi(n)
+        monkeypatch.setenv("NUFI_B200_CLUSTER", "1")
+        s.step(n)
+        assert np.array_equal(lvl_pair, s.download_phi(n))
+
+
 @pytest.mark.parametrize("name", ["1d-two-stream", "2d-landau", "3d-landau"])
 def test_partial_ranges_accumulate(name, histories, oracle):
     """compute_rho/download_rho keep the reference GPU convention: partial = -dV*sum f, download accumulates;

@@ -90,11 +90,12 @@ def model(body):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    path = args[0] if args else LIB
+    argv = sys.argv[1:]
     want = None
-    if "--kernels" in sys.argv:
-        want = sys.argv[sys.argv.index("--kernels") + 1:]
+    if "--kernels" in argv:
+        want = argv[argv.index("--kernels") + 1:]
+        argv = argv[:argv.index("--kernels")]
+    path = argv[0] if argv else LIB
     sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
     funcs = re.split(r"\n\s*Function : ", sass)[1:]
     print(f"# register-file operand model of the FP64 hot loops in {os.path.relpath(path, ROOT) if path.startswith(ROOT) else path}")

@@ -57,6 +57,19 @@ def halfwarp_degree(c):
     return deg
 
 
+def halfwarp_degree_classes(c, cls):
+    """c, cls: [..., 16] cells and their bank classes -> max number of DISTINCT cells per class."""
+    order = np.argsort(c, axis=-1)
+    c = np.take_along_axis(c, order, axis=-1)
+    cls = np.take_along_axis(cls, order, axis=-1)
+    first = np.ones(c.shape, dtype=bool)
+    first[..., 1:] = c[..., 1:] != c[..., :-1]
+    deg = np.zeros(c.shape[:-1], dtype=np.int64)
+    for r in range(16):
+        deg = np.maximum(deg, np.sum(first & (cls == r), axis=-1))
+    return deg
+
+
 def group_degree(c, lanes):
     """c: [..., lanes] cells of one wavefront group (16 lanes for a 64-bit load, 8 for a 128-bit load whose lane stride is 16 B):
     max number of DISTINCT cells per residue class mod `lanes` = wavefronts that group's load takes."""
@@ -92,6 +105,46 @@ def main():
     now = 3 * 2 * base / ideal
     print(f"wavefronts per warp-step: now (3 x LDS.64) {now:.2f};  (p0,p1) as one LDS.128 + p2 as LDS.64: {4 * r128 + 2 * base / ideal:.2f};"
           f"  two LDS.128 (padded cell): {8 * r128:.2f};  conflict-free floor 6")
+    # (i) a second copy of every staged level at a different bank phase, the lane picks the copy by (cell >> 4) & 1
+    #     (round-1 review's experiment): class(c) = (c + 8 * ((c >> 4) & 1)) mod 16 -- cells 16 apart no longer collide, but cells
+    #     8 and 24 apart now do: a half-warp stretched over more than 16 cells has more lanes than free classes either way
+    c64 = hw.astype(np.int64)
+    alt = c64 + 8 * ((c64 >> 4) & 1)
+    deg_i = halfwarp_degree_classes(c64, alt & 15)
+    print(f"(i) two copies, bank phase by (cell>>4)&1: wavefront ratio {deg_i.sum() / deg_i.size:.3f} (baseline {base / ideal:.3f})")
+    # (i') four copies at phases 0,4,8,12 by (cell>>4)&3
+    alt4 = c64 + 4 * ((c64 >> 4) & 3)
+    deg_i4 = halfwarp_degree_classes(c64, alt4 & 15)
+    print(f"(i') four copies, phase by (cell>>4)&3:     wavefront ratio {deg_i4.sum() / deg_i4.size:.3f}")
+    # (ii) re-pack the lanes of a CTA-round (one tile, the 15 warps x 2 points of a round = 30 velocities spread over the velocity
+    #      range, 32 nodes each = 960 points) so that the 16 lanes of every half-warp have distinct cells mod 16: the best any
+    #      re-packing can do at the level it is made for is max(ceil(P/16), largest residue class) half-warp loads for P points;
+    #      one level later the points have moved by v*dt/dx cells -- a different amount for every velocity -- and the packing is
+    #      as good as random.  Measured: ideal packing at the level itself, then the SAME packing 1, 2, 4 levels later.
+    rng = np.random.default_rng(0)
+    vel_sets = [np.arange(j, Nu, 18)[:30] for j in range(0, 18, 3)]  # interleaved velocity sets like a CTA-round's
+    levels = [100, 300, 500, 700]
+    stats = {0: [], 1: [], 2: [], 4: []}
+    for m0 in levels:
+        for t in range(Nx // 32):
+            for vs in vel_sets:
+                pts = cells[m0, 32 * t:32 * t + 32][:, vs].reshape(-1)
+                P_ = (pts.size // 16) * 16
+                nh = P_ // 16
+                order = np.argsort(pts[:P_] & 15, kind="stable")  # deal the residues round-robin into the half-warps
+                groups = np.empty(P_, dtype=np.int64)
+                groups[order] = np.arange(P_) % nh
+                slot = np.empty(P_, dtype=np.int64)
+                slot[order] = np.arange(P_) // nh
+                for lag in stats:
+                    if m0 + lag >= L:
+                        continue
+                    later = cells[m0 + lag, 32 * t:32 * t + 32][:, vs].reshape(-1)[:P_].astype(np.int64)
+                    g = np.zeros((nh, 16), dtype=np.int64)
+                    g[groups, slot] = later
+                    stats[lag].append(halfwarp_degree(g).mean())
+    print("(ii) re-packed half-warps (dealt by cell mod 16): wavefront ratio at the level of the re-pack / 1 / 2 / 4 levels later: " +
+          " / ".join(f"{np.mean(stats[k]):.2f}" for k in (0, 1, 2, 4)))
     span = tiles.max(axis=-1).astype(np.int64) - tiles.min(axis=-1)
     print("warp span in cells (32 lanes, 31 = rigid): percentiles 50/90/99:", np.percentile(span, [50, 90, 99]))
 
