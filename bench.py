@@ -40,6 +40,10 @@ FLOP_PER_POINT_STEP = {1: 30.0, 2: 138.0, 3: 431.0}  # SURVEY.md section 8d / Ap
 NCU_DRAM_TRAFFIC_BYTES = {"C2": 4.98e6, "C3": 3.65e6, "C4": 1.62e6, "C5-16": 1.44e6, "C5-32": 8.73e6}
 SMEM_BYTES_PER_POINT_STEP = {1: 24.0, 2: 128.0, 3: 512.0}  # coefficients a point gathers per level
 SMEM_BYTES_PER_CLK_SM = 128.0  # shared-memory data pipe; tools/microbench.cu measures 125-127 on this GPU
+# FP64 ceiling of each kernel's hot loop once the register-file operand reads of its DFMAs are counted (a DFMA with 1 / 2 / 3
+# fresh 64-bit register operands issues every 2.00 / 2.17 / 3.00 cycles, profiles/r02_microbench.txt), as a fraction of the DFMA
+# peak; tools/sass_rf_model.py on the built library -> profiles/r02_sass_rf_model.txt.  Keys: (dim, xpp level format)
+RF_CEILING = {(1, False): 0.848, (2, True): 0.809, (2, False): 0.825, (3, True): 0.780, (3, False): 0.793}
 L2_FLUSH_BYTES = 256 << 20
 RHO_TOL = 1e-10
 ALIGN_RANKS = True  # N > 1: a stream-ordered NCCL barrier between the (untimed) L2 flush and every timed step
@@ -529,7 +533,8 @@ def measure_workload(name, scaling, rank, world, local, args, flush, torch, dist
             ex = {"workload": desc, "scaling": scaling if world > 1 else None, "depth_n": depth, "n_quad": n_quad(conf),
                   "point_steps_per_s": ps * steps / (m["t_ms"] * 1e-3), "ms_per_step": m["t_ms"] / steps, "steps": steps,
                   "kernel_ms": m["bt_ms"], "kernel_ms_per_rank": m["bt_ms_per_rank"], "variant": r.s.last_variant, "exchange": r.exchange,
-                  "fp64_tflops_per_gpu": tf, "fp64_frac": tf / peak_tf, "parity": parity}
+                  "fp64_tflops_per_gpu": tf, "fp64_frac": tf / peak_tf,
+                  "frac_of_rf_ceiling": tf / peak_tf / RF_CEILING.get((conf.dim, "/xpp" in r.s.last_variant), 1.0), "parity": parity}
             if with_ref_cuda and not args.no_cpu:
                 rc = reference_cuda_leg(conf, f0, depth, hist, None, local, reps=1 if (conf.dim == 3 and conf.Nx >= 32) else 2)
                 ex["reference_cuda_point_steps_per_s"] = rc.get("value")
@@ -662,6 +667,10 @@ def run_gpu_arm(args):
             "ms_per_step_with_kernel_events": m["t_ms_kernel_timing"] / args.steps,
             "how": "second timed region of the same K steps with a CUDA event pair around every backtrace launch (library stream)",
             "flop_per_point_step": FLOP_PER_POINT_STEP[dim],
+            "rf_ceiling": RF_CEILING.get((dim, "/xpp" in variant)),
+            "frac_of_rf_ceiling": (achieved_tf / peak_tf / RF_CEILING[(dim, "/xpp" in variant)]) if (dim, "/xpp" in variant) in RF_CEILING else None,
+            "rf_ceiling_note": "FP64 ceiling of this kernel's hot loop with the register-file operand reads of its DFMAs counted "
+                               "(DESIGN.md 3.1, profiles/r02_sass_rf_model.txt); in 1d shared memory binds first",
             "peak_source": "measured live: register-only DFMA loop (nufi_b200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
             "smem": {"achieved": my_psteps * SMEM_BYTES_PER_POINT_STEP[dim] / (m["bt_ms"] * 1e-3) / 1e9,
                      "peak": SMEM_BYTES_PER_CLK_SM * s_sm_count * sm_mhz_peak * 1e6 / 1e9, "unit": "GB/s",

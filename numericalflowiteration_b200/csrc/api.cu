@@ -127,7 +127,7 @@ int create_common(const nufi_b200_config3d &c, int dim, int order, const nufi_b2
         h->sxy = dim >= 2 ? h->sx * static_cast<int>(c.Ny + halo) : 0;
         h->level_stride = (h->stride_t + 1) & ~size_t(1);
     } else if (dim == 1) {
-        h->level_stride = (3 * c.Nx + 1) & ~size_t(1); // per-cell quadratics [p0 p1 p2] (tail.cu), 16-byte multiple
+        h->level_stride = (3 * c.Nx + 1) & ~size_t(1); // per-cell quadratics [Nx x (p1, p2)] [Nx x p0] (tail.cu), 16-byte multiple
         h->raw_stride = (c.Nx + 3 + 1) & ~size_t(1);
         h->sx = 0; h->sxy = 0;
     } else {

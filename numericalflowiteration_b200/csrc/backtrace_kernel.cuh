@@ -74,6 +74,12 @@ template <bool STAGED> __device__ __forceinline__ double ld(const double *p)
     else return __ldg(p);
 }
 
+template <bool STAGED> __device__ __forceinline__ double2 ld2(const double2 *p)
+{
+    if constexpr (STAGED) return *p;
+    else return __ldg(p);
+}
+
 // physical coordinate -> (cell, centred offset), the reference's wrap/locate arithmetic (nufi/fields.hpp:315-331)
 __device__ __forceinline__ void locate(double x, double x_min, double L, double L_inv, double dx_inv, int N, int &k, double &tau)
 {
@@ -140,8 +146,11 @@ template <int KIND, bool STAGED, bool POW2>
 __device__ __forceinline__ void step1d(Point<1> &p, const double *lev, const BtParams &P, unsigned &bad)
 {
     if constexpr (KIND != FIRST) relocate<POW2>(p.tau[0], p.cell[0], fma(P.ncx, p.vel[0], p.tau[0]), P.Nx, bad);
-    const double *c = lev + 3 * p.cell[0];
-    const double p0 = ld<STAGED>(c), p1 = ld<STAGED>(c + 1), p2 = ld<STAGED>(c + 2);
+    // level = [Nx x (p1, p2)] [Nx x p0]: one 128-bit and one 64-bit load per point-step (a 128-bit load is served per quarter-warp:
+    // eight lanes instead of sixteen have to fall on distinct banks, profiles/r02_c2_bank_conflicts.txt).  (p1, p2) feed the first
+    // FMA of the kick; p0, whose address costs one more add, is only needed by the second.
+    const double2 p12 = ld2<STAGED>(reinterpret_cast<const double2 *>(lev) + p.cell[0]);
+    const double p1 = p12.x, p2 = p12.y, p0 = ld<STAGED>(lev + 2 * P.Nx + p.cell[0]);
     const double t = p.tau[0];
     const double q = fma(t, p2, p1);
     if constexpr (KIND == FULL) p.vel[0] = fma(t, q, p0 + p.vel[0]);
@@ -322,12 +331,6 @@ __device__ __forceinline__ void step_generic(Point<DIM> &p, const double *lev, c
 // window row becomes two Horner evaluations (value: 3 FMA, derivative A' = a1 + 2 tau (a2 + 1.5 tau a3): 2 FMA) instead of
 // eight FMAs plus the x basis; loads are 2 x 128-bit per row, conflict-free for consecutive cells.  P.gx carries the 1/3
 // of A' = 3 sum_a c_a 2 N'_a.
-template <bool STAGED> __device__ __forceinline__ double2 ld2(const double2 *p)
-{
-    if constexpr (STAGED) return *p;
-    else return __ldg(p);
-}
-
 template <int KIND, bool STAGED, bool POW2>
 __device__ __forceinline__ void step2d_xpp(Point<2> &p, const double *lev, const BtParams &P, unsigned &bad)
 {

@@ -187,8 +187,8 @@ __global__ void expand_kernel(const double *src, double *level, ExpandParams E, 
     }
 }
 
-// 1d: raw level with halo + per-cell quadratics, 3 consecutive doubles [p0 p1 p2] per cell (a stride of 3 doubles
-// keeps the 64-bit shared-memory loads of a warp's consecutive cells conflict-free).
+// 1d: raw level with halo + per-cell quadratics p0 + p1 tau + p2 tau^2, stored as [Nx x (p1, p2)] [Nx x p0]: one 128-bit and one
+// 64-bit shared-memory load per point-step, both conflict-free for a warp's consecutive cells.
 __global__ void expand1d_kernel(const double *src, double *raw, double *pp, ExpandParams E, const double *epart,
                                 unsigned n_epart, double vol_half, double *energy_out)
 {
@@ -200,9 +200,9 @@ __global__ void expand1d_kernel(const double *src, double *raw, double *pp, Expa
 #pragma unroll
         for (int a = 0; a < 4; ++a) c[a] = src[(k + a) % Nx];
         cell_poly_1d(c, E.g1, p0, p1, p2);
-        pp[3 * k] = p0;
-        pp[3 * k + 1] = p1;
-        pp[3 * k + 2] = p2;
+        pp[2 * k] = p1; // level = [Nx x (p1, p2)] [Nx x p0]
+        pp[2 * k + 1] = p2;
+        pp[2 * Nx + k] = p0;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && (3 * Nx) % 2) pp[3 * Nx] = 0; // padding double
     if (energy_out && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -220,9 +220,9 @@ __global__ void ref_to_device_kernel(const double *ref, double *level, double *r
         for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < E.Nx; k += gridDim.x * blockDim.x) {
             double p0, p1, p2;
             cell_poly_1d(ref + k, E.g1, p0, p1, p2);
-            level[3 * k] = p0;
-            level[3 * k + 1] = p1;
-            level[3 * k + 2] = p2;
+            level[2 * k] = p1;
+            level[2 * k + 1] = p2;
+            level[2 * E.Nx + k] = p0;
         }
         if (blockIdx.x == 0 && threadIdx.x == 0 && (3 * E.Nx) % 2) level[3 * E.Nx] = 0;
         return;
@@ -616,9 +616,9 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
 #pragma unroll
             for (int a = 0; a < 4; ++a) c[a] = cur[(k + a) % Nx].x;
             cell_poly_1d(c, E.g1, p0, p1, p2);
-            S.level[3 * k] = p0;
-            S.level[3 * k + 1] = p1;
-            S.level[3 * k + 2] = p2;
+            S.level[2 * k] = p1;
+            S.level[2 * k + 1] = p2;
+            S.level[2 * Nx + k] = p0;
         }
         if (threadIdx.x == 0 && (3 * Nx) % 2) S.level[3 * Nx] = 0;
     } else if (E.xpp) {
