@@ -46,6 +46,8 @@ SMEM_BYTES_PER_CLK_SM = 128.0  # shared-memory data pipe; tools/microbench.cu me
 RF_CEILING = {(1, False): 0.848, (2, True): 0.809, (2, False): 0.825, (3, True): 0.780, (3, False): 0.793}
 L2_FLUSH_BYTES = 256 << 20
 RHO_TOL = 1e-10
+SETTLE_STEPS = 10  # untimed iterations in front of every timed region (at least the W asked for): the first steps after an idle
+# gap run 1-3 % slower (clock / power ramp), config.settle_steps states it
 ALIGN_RANKS = True  # N > 1: a stream-ordered NCCL barrier between the (untimed) L2 flush and every timed step
 
 
@@ -327,7 +329,7 @@ def timed_region(runner, n, steps, warmup, flush, torch, dist, sampler=None, ali
     """`warmup` untimed steps, then `steps` fused steps at depth n, each bracketed by a CUDA event pair on the stream the
     library launches on, with an (untimed) L2 flush in front of each.  Returns (sum of step times in ms, max over ranks; launches)."""
     s, st = runner.s, runner.stream
-    for _ in range(warmup):  # untimed, same shape as the timed iterations below
+    for _ in range(max(warmup, SETTLE_STEPS)):  # untimed, same shape as the timed iterations below
         with torch.cuda.stream(st):
             if flush is not None:
                 flush.fill_(1.0)
@@ -695,6 +697,7 @@ def run_gpu_arm(args):
                               "flushed between timed steps (256 MiB fill, untimed; steps timed individually with CUDA events)" +
                               ("; ranks aligned by a stream-ordered NCCL barrier between the flush and each timed step (untimed)"
                                if world > 1 and ALIGN_RANKS else "")),
+                       "settle_steps": max(args.warmup, SETTLE_STEPS),
                        "parallelism": (f"quadrature points sharded over {world} GPU(s); rho exchange: " +
                                        ("stores into NVLink peer memory fused into the slot-reduction and tail kernels (no collective call)"
                                         if runner.exchange == "peer-memory" else "NCCL all-reduce")) if world > 1 else "1 GPU",
