@@ -93,6 +93,8 @@ public:
 
     // beyond the reference
     void step(size_t n) { ck(nufi_b200_step(h_, n)); }
+    // the reference drivers' loop body in one call, history on the host: returns the electric energy of step n
+    double step_host(size_t n, double *coeffs, double *rho = nullptr) { double e = 0; ck(nufi_b200_step_host(h_, n, coeffs, rho, &e, 0)); return e; }
     void eval_rho_all(size_t n, double *rho) { ck(nufi_b200_eval_rho_all(h_, n, rho)); }
     double solve_interpolate(size_t n) { double e = 0; ck(nufi_b200_solve_interpolate(h_, n, &e)); return e; }
     double electric_energy(size_t n) { double e = 0; ck(nufi_b200_download_energy(h_, n, n + 1, &e)); return e; }

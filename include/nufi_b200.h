@@ -150,6 +150,12 @@ int nufi_b200_interpolate(nufi_b200_handle *h, const double *values_host, double
 /* ---- fused step: backtrace + reduce + Poisson + interpolate + store level n, no host round trip.
  *      Asynchronous; the electric energy of step n is kept on the device (nufi_b200_download_energy). ---- */
 int nufi_b200_step(nufi_b200_handle *h, size_t n);
+/* The same step for a caller that keeps the history on the HOST -- the loop body of the reference's GPU drivers in one call
+ * (upload_phi(n-1) / compute_rho / download_rho / [MPI_Allreduce] / poisson.solve / interpolate, bin/test_nufi_gpu_3d.cpp:154-162):
+ * level n-1 is copied from coeffs_base to the device (n > 0; lower levels were pushed by earlier calls or upload_phi), the fused
+ * step runs, level n is written to coeffs_base + n*stride_t, rho (CPU convention, may be NULL) and the electric energy (may be
+ * NULL) come back with it; one stream synchronisation, blocking.  peer != 0: the multi-GPU step (nufi_b200_peer_step). */
+int nufi_b200_step_host(nufi_b200_handle *h, size_t n, double *coeffs_base, double *rho_host, double *energy, int peer);
 /* blocking; energies[i] = electric energy of step n_begin+i, for steps run by step/solve_interpolate */
 int nufi_b200_download_energy(nufi_b200_handle *h, size_t n_begin, size_t n_end, double *energies);
 /* blocking; rho of the most recent step / peer_step / group_step / eval_rho_all as the field tail consumed it: CPU convention

@@ -16,7 +16,7 @@ SYMBOLS = [
     "nufi_b200_create_1d", "nufi_b200_create_2d", "nufi_b200_create_3d", "nufi_b200_destroy", "nufi_b200_last_error",
     "nufi_b200_compute_rho", "nufi_b200_download_rho", "nufi_b200_upload_phi", "nufi_b200_compute_metrics",
     "nufi_b200_download_metrics", "nufi_b200_eval_rho_all", "nufi_b200_solve_interpolate",
-    "nufi_b200_solve_interpolate_host", "nufi_b200_poisson_solve", "nufi_b200_interpolate", "nufi_b200_step", "nufi_b200_download_energy", "nufi_b200_download_phi",
+    "nufi_b200_solve_interpolate_host", "nufi_b200_poisson_solve", "nufi_b200_interpolate", "nufi_b200_step", "nufi_b200_step_host", "nufi_b200_download_energy", "nufi_b200_download_phi",
     "nufi_b200_sync", "nufi_b200_download_history", "nufi_b200_upload_history", "nufi_b200_eval_f",
     "nufi_b200_eval_field", "nufi_b200_set_stream", "nufi_b200_rho_device", "nufi_b200_field_tail_device",
     "nufi_b200_launch_count", "nufi_b200_last_backtrace_ms", "nufi_b200_backtrace_time", "nufi_b200_last_variant", "nufi_b200_set_variant",
@@ -59,7 +59,7 @@ def load() -> C.CDLL:
     for name, args in {
         "compute_rho": [vp, sz, sz, sz], "download_rho": [vp, vp], "upload_phi": [vp, sz, vp],
         "compute_metrics": [vp, sz, sz, sz], "download_metrics": [vp, vp], "eval_rho_all": [vp, sz, vp],
-        "solve_interpolate": [vp, sz, vp], "solve_interpolate_host": [vp, sz, vp, vp], "step": [vp, sz],
+        "solve_interpolate": [vp, sz, vp], "solve_interpolate_host": [vp, sz, vp, vp], "step": [vp, sz], "step_host": [vp, sz, vp, vp, vp, i],
         "download_energy": [vp, sz, sz, vp], "download_phi": [vp, sz, vp], "sync": [vp], "set_stream": [vp, vp],
         "rho_device": [vp, C.POINTER(vp)], "field_tail_device": [vp, sz, vp], "last_backtrace_ms": [vp, C.POINTER(C.c_float)],
         "set_variant": [vp, i], "measure_fp64_peak": [i, dp], "set_kernel_timing": [vp, i], "set_tile_nodes": [vp, i],

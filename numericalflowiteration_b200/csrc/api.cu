@@ -192,7 +192,7 @@ int create_common(const nufi_b200_config3d &c, int dim, int order, const nufi_b2
     CREATE_CHECK(cudaMemsetAsync(h->d_done, 0, sizeof(unsigned int), h->stream));
     CREATE_CHECK(cudaMalloc(&h->d_ll_status, sizeof(int)));
     CREATE_CHECK(cudaMemsetAsync(h->d_ll_status, 0, sizeof(int), h->stream));
-    h->h_pinned_cap = h->stride_t > h->n_nodes ? h->stride_t : h->n_nodes;
+    h->h_pinned_cap = h->stride_t + h->n_nodes + 2; // step_host returns a level, rho and the energy with one copy-back
     if (h->h_pinned_cap < c.Nt + 1) h->h_pinned_cap = c.Nt + 1;
     CREATE_CHECK(cudaMallocHost(&h->h_pinned, h->h_pinned_cap * sizeof(double)));
     CREATE_CHECK(cudaMallocHost(&h->h_up, h->h_pinned_cap * sizeof(double)));
@@ -462,6 +462,34 @@ int nufi_b200_step(nufi_b200_handle *h, size_t n)
     rc = launch_backtrace(hh, n, 0, hh->n_nodes * hh->n_vel, false, /*defer_finish=*/true);
     if (rc) return rc;
     return tail_run(hh, n, nullptr);
+}
+
+// One time step for a caller that owns the history on the HOST (the reference drivers' loop body, bin/test_nufi_gpu_3d.cpp:
+// 154-162, in one call): level n-1 host -> device (the only level the device has not seen: levels below were pushed by
+// earlier calls), fused step on the device, level n + rho + energy device -> host, ONE stream synchronisation.
+int nufi_b200_step_host(nufi_b200_handle *h, size_t n, double *coeffs_base, double *rho_host, double *energy, int peer)
+{
+    ENTER(h);
+    if (n > hh->Nt) return fail(hh, NUFI_B200_ERR_RANGE, "Time-step out of range.");
+    if (!coeffs_base) return fail(hh, NUFI_B200_ERR_ARG, "coeffs is NULL");
+    int rc;
+    if (n > 0) {
+        rc = nufi_b200_upload_phi(h, n - 1, coeffs_base);
+        if (rc) return rc;
+    }
+    rc = peer ? nufi_b200_peer_step(h, n) : nufi_b200_step(h, n);
+    if (rc) return rc;
+    rc = convert_level_from_device(hh, n, hh->d_stage);
+    if (rc) return rc;
+    double *lvl = hh->h_pinned, *rho = lvl + hh->stride_t, *en = rho + hh->n_nodes;
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(lvl, hh->d_stage, sizeof(double) * hh->stride_t, cudaMemcpyDeviceToHost, hh->stream));
+    if (rho_host) NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(rho, hh->d_rho_full, sizeof(double) * hh->n_nodes, cudaMemcpyDeviceToHost, hh->stream));
+    NUFI_CUDA_CHECK(hh, cudaMemcpyAsync(en, hh->d_energy + n, sizeof(double), cudaMemcpyDeviceToHost, hh->stream));
+    NUFI_CUDA_CHECK(hh, cudaStreamSynchronize(hh->stream));
+    std::memcpy(coeffs_base + n * hh->stride_t, lvl, sizeof(double) * hh->stride_t);
+    if (rho_host) std::memcpy(rho_host, rho, sizeof(double) * hh->n_nodes);
+    if (energy) *energy = *en;
+    return NUFI_B200_OK;
 }
 
 int nufi_b200_download_energy(nufi_b200_handle *h, size_t n_begin, size_t n_end, double *energies)

@@ -43,6 +43,42 @@ def test_checkpoint_restart_is_bit_identical(name, tmp_path):
         assert np.array_equal(got_energy, want_energy[k:]), (name, loader)
 
 
+@pytest.mark.parametrize("name", ["1d-two-stream", "2d-landau", "3d-bump"])
+def test_step_host_is_the_fused_step_with_a_host_history(name, oracle):
+    """nufi_b200_step_host (the reference GPU drivers' loop body in one call, history kept by the caller on the host): a free run
+    through it fills the host array with the same levels, bit for bit, as the device-resident fused steps, returns the same
+    energies and the rho of every step (checked against the oracle's eval_rho on that history)."""
+    mk, f0 = CASES[name]
+    conf = mk()
+    st = stride_t(conf)
+    with CudaScheduler(conf, f0) as s:
+        for n in range(conf.Nt):
+            s.step(n)
+        want_hist = s.download_history(conf.Nt)
+        want_energy = s.download_energy(0, conf.Nt)
+    host = np.zeros((conf.Nt + 1) * st)
+    with CudaScheduler(conf, f0) as s:
+        rho = np.zeros(s.n_nodes)
+        energies = []
+        for n in range(conf.Nt):
+            energies.append(s.step_host(n, host, rho))
+            if n in (1, conf.Nt - 1):
+                assert rel_linf(rho, oracle.rho(conf, f0, n, host)) <= 1e-10
+        with pytest.raises(RangeError):
+            s.step_host(conf.Nt + 1, host)
+    assert np.array_equal(host[: conf.Nt * st], want_hist[: conf.Nt * st]), name
+    assert np.array_equal(np.array(energies), want_energy), name
+    # a fresh handle continues from the host history alone: the levels it has not seen come in through upload_phi / step_host
+    with CudaScheduler(conf, f0) as s:
+        k = conf.Nt // 2
+        s.upload_history(host, k)
+        redo = host.copy()
+        redo[k * st:] = 0
+        for n in range(k, conf.Nt):
+            s.step_host(n, redo)
+    assert np.array_equal(redo[: conf.Nt * st], host[: conf.Nt * st]), name
+
+
 @pytest.mark.parametrize("name", ["1d-two-stream", "2d-landau", "3d-landau"])
 @pytest.mark.parametrize("xpp", [0, 1])
 def test_sampling_matches_reference_point_functions(name, xpp, oracle, monkeypatch):
