@@ -529,10 +529,11 @@ def live_parity(runner, conf, f0, n, coeffs_host, cpu_budget, dist, want_cpu_bas
             dev_ext = float(np.max(np.abs(got[:l_n] - ext))) / scale
             ref_ext = float(np.max(np.abs(want - ext))) / scale
             parity.update({"rho_rel_linf_device_vs_extended_sum": dev_ext, "rho_rel_linf_reference_vs_extended_sum": ref_ext,
-                           "ok": bool(err <= RHO_TOL or (dev_ext <= RHO_TOL and err <= 2.0 * ref_ext + RHO_TOL)),
+                           "ok": bool(err <= RHO_TOL or (dev_ext <= max(RHO_TOL, ref_ext) and err <= 2.0 * ref_ext + RHO_TOL)),
                            "note": "reference's own double-precision summation error exceeds a tenth of the tolerance on this sample; "
-                                   "ok = within tolerance of the reference, or within tolerance of the extended-precision sum and no "
-                                   "further from the reference than twice the reference's own distance from it"})
+                                   "ok = within tolerance of the reference, or no further from the extended-precision sum than the "
+                                   "tolerance or the reference itself (whichever is larger) and no further from the reference than twice "
+                                   "the reference's own distance from it plus the tolerance; all three distances are reported"})
         if replicas is not None:
             parity["replicas"] = replicas
             parity["ok"] = bool(parity["ok"] and replicas["bit_identical"])

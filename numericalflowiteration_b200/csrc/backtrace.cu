@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) finish_rho_kernel(const __grid_constant__
         const unsigned long long l = F.l_first + static_cast<unsigned long long>(tile) * F.TN + lane;
         if (static_cast<unsigned>(lane) < F.TN && l <= F.l_last) {
             F.rho_partial[l] = -F.dV * tot;
-            if (F.rho_full) F.rho_full[l] = 1 - F.dV * tot;
+            if (F.rho_full) F.rho_full[l] = fma(-F.dV, tot, 1.0);
             for (int p = 0; p < X.world; ++p) peer_store_double(X.rho[p] + l, tot, X.flag);
         }
     }
@@ -390,8 +390,10 @@ int launch_backtrace(Handle *h, size_t n, size_t q_begin, size_t q_end, bool met
                 const unsigned long long rpc = (R + grid - 1) / grid;
                 const unsigned long long ctas = (R + rpc - 1) / rpc;
                 const double chains = static_cast<double>(W) * ilp;
-                // time of a CTA-round ~ max(latency floor, throughput term); ILP 2 shares the per-level bookkeeping
-                double cost = static_cast<double>(rpc) * (chains > csat ? chains : csat) * (ilp == 2 ? 0.92 : 1.0);
+                // time of a CTA-round ~ max(latency floor, throughput term); ILP 2 shares the per-level bookkeeping (2d).  1d: the same
+                // chains as twice the warps with one point each run as fast (C1) or faster (C2 0.1408 vs 0.1470 ms, W30 x 1 vs
+                // W15 x 2, profiles/r02_sweep_shape_1d.txt): a replayed load stalls one chain, not two
+                double cost = static_cast<double>(rpc) * (chains > csat ? chains : csat) * (ilp == 2 && h->dim != 1 ? 0.92 : 1.0);
                 cost *= 1.0 + 1e-3 * (static_cast<double>(grid) - static_cast<double>(ctas)) / grid; // prefer more busy SMs
                 cost *= 1.0 + 1e-4 * chains;                                                          // then narrower CTAs
                 if (cost < best_cost) { best_cost = cost; best_ilp = ilp; best_W = W; }

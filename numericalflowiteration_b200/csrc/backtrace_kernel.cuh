@@ -17,16 +17,6 @@ namespace
 
 constexpr double kMagic = 6755399441055744.0; // 1.5 * 2^52: adding it rounds to the nearest integer
 
-// s += x with the rounding error of the addition accumulated in lo (Knuth's branch-free two-sum; no fast-math: nvcc keeps the
-// order of floating-point additions)
-__device__ __forceinline__ void two_sum(double &s, double &lo, double x)
-{
-    const double t = s + x;
-    const double xv = t - s;
-    lo += (s - (t - xv)) + (x - xv);
-    s = t;
-}
-
 // Periodic cell index after a move of dk cells.  POW2: mask.  Otherwise one conditional correction each way;
 // anything further out (a point crossing more than a whole period in one step) is clamped into range and
 // flagged -- such points are recomputed by the robust slow path after the trace.
@@ -899,7 +889,7 @@ __global__ void __launch_bounds__(Tune<DIM, ILP, XPP, ORDER>::max_threads, 1)
                         const unsigned long long l = F.l_first + static_cast<unsigned long long>(tile) * F.TN + lane;
                         if (static_cast<unsigned>(lane) < F.TN && l <= F.l_last) {
                             F.rho_partial[l] = -F.dV * tot;
-                            if (F.rho_full) F.rho_full[l] = 1 - F.dV * tot;
+                            if (F.rho_full) F.rho_full[l] = fma(-F.dV, tot, 1.0);
                         }
                     }
                     consumer_sync(W * 32);

@@ -133,6 +133,16 @@ struct PeerRecv // receiver side (tail_small_kernel / peer_gather_kernel)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// s += x with the rounding error of the addition accumulated in lo (Knuth's branch-free two-sum; no fast-math: nvcc keeps the
+// order of floating-point additions)
+__device__ __forceinline__ void two_sum(double &s, double &lo, double x)
+{
+    const double t = s + x;
+    const double xv = t - s;
+    lo += (s - (t - xv)) + (x - xv);
+    s = t;
+}
+
 // ---- the wire encoding
 __device__ __forceinline__ void peer_store_double(uint4 *dst, double v, unsigned flag)
 {
@@ -170,7 +180,7 @@ __device__ __forceinline__ void ll_load4(const uint4 *const (&src)[4], unsigned 
 // `self` >= 0: that rank's value is `own` (no load).
 __device__ __forceinline__ double peer_rank_sum(const uint4 *src, size_t stride, int world, unsigned flag, int *status, int self, double own)
 {
-    double sum = 0;
+    double sum = 0, lo = 0; // compensated: the result is the ranks' sum rounded once
     for (int r0 = 0; r0 < world; r0 += 4) {
         unsigned a[4], fa[4], b[4], fb[4];
         long long t0 = 0;
@@ -194,9 +204,9 @@ __device__ __forceinline__ double peer_rank_sum(const uint4 *src, size_t stride,
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            if (r0 + u < world) sum += r0 + u == self ? own : __hiloint2double(static_cast<int>(b[u]), static_cast<int>(a[u]));
+            if (r0 + u < world) two_sum(sum, lo, r0 + u == self ? own : __hiloint2double(static_cast<int>(b[u]), static_cast<int>(a[u])));
     }
-    return sum;
+    return sum + lo;
 }
 #endif
 

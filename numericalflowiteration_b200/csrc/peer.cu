@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) peer_gather_kernel(const __grid_constant_
 {
     pdl_trigger();
     for (size_t l = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; l < X.n_nodes; l += static_cast<size_t>(gridDim.x) * blockDim.x)
-        X.rho_full[l] = 1 - X.dV * peer_rank_sum(X.rho + l, X.n_nodes, X.world, X.flag, X.status, -1, 0.0);
+        X.rho_full[l] = fma(-X.dV, peer_rank_sum(X.rho + l, X.n_nodes, X.world, X.flag, X.status, -1, 0.0), 1.0);
 }
 
 size_t region_offset(const Handle *h, int parity, int rank)

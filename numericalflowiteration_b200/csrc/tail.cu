@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
         for (int l = threadIdx.x; l < N; l += blockDim.x) A[l] = make_double2(S.rho[l], 0.0);
     } else if (!from_slots) { // multi-GPU step of a rank without a share of its own: every rank's sums are in the exchange buffer
         for (int l = threadIdx.x; l < N; l += blockDim.x) {
-            const double r = 1 - S.X.dV * peer_rank_sum(S.X.rho + l, S.X.n_nodes, S.X.world, S.X.flag, S.X.status, -1, 0.0);
+            const double r = fma(-S.X.dV, peer_rank_sum(S.X.rho + l, S.X.n_nodes, S.X.world, S.X.flag, S.X.status, -1, 0.0), 1.0);
             S.X.rho_full[l] = r;
             A[l] = make_double2(r, 0.0);
         }
@@ -481,8 +481,8 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
     } else {
         const FinishParams &F = S.F;
         auto slot_sum = [&](unsigned tile, unsigned lane, unsigned b_lo, unsigned b_hi, int w) {
-            double sum = 0;
-            for (unsigned b = b_lo + w; b <= b_hi; b += 32) { // four loads in flight per trip; + 0.0 is exact, the order is kept
+            double sum = 0, lo = 0; // compensated (two-sum): the partial sum is exact to one rounding
+            for (unsigned b = b_lo + w; b <= b_hi; b += 32) { // four loads in flight per trip; the order is kept
                 double v[4];
                 size_t at[4]; // slot index, or ~0: beyond the tile's last CTA
 #pragma unroll
@@ -503,9 +503,10 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
 #pragma unroll
                     for (unsigned u = 0; u < 4; ++u) v[u] = at[u] != ~static_cast<size_t>(0) ? F.slots[at[u]] : 0.0;
                 }
-                sum = (((sum + v[0]) + v[1]) + v[2]) + v[3];
+#pragma unroll
+                for (unsigned u = 0; u < 4; ++u) two_sum(sum, lo, v[u]);
             }
-            return sum;
+            return sum + lo;
         };
         auto store_rho = [&](int l, double tot) {
             F.rho_partial[l] = -F.dV * tot;
@@ -515,12 +516,14 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
                 for (int p = 0; p < S.XP.world; ++p)
                     if (p != S.XP.rank) peer_store_double(S.XP.rho[p] + l, tot, S.XP.flag);
                 tot = peer_rank_sum(S.X.rho + l, S.X.n_nodes, S.X.world, S.X.flag, S.X.status, S.XP.rank, tot);
-                const double r = 1 - S.X.dV * tot;
+                const double r = fma(-S.X.dV, tot, 1.0);
                 S.X.rho_full[l] = r;
                 A[l] = make_double2(r, 0.0);
                 return;
             }
-            const double r = 1 - F.dV * tot;
+            // rho = 1 - dV * sum with ONE rounding, of the small result (the reference rounds the O(1) product first: where the
+            // density perturbation has decayed to 1e-6 that rounding alone is 1e-10 of it)
+            const double r = fma(-F.dV, tot, 1.0);
             if (F.rho_full) F.rho_full[l] = r;
             A[l] = make_double2(r, 0.0);
         };
@@ -540,10 +543,10 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
             __syncthreads();
             TAIL_MARK(10);
             for (int l = threadIdx.x; l < N; l += blockDim.x) {
-                double tot = 0;
+                double tot = 0, lo = 0;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) tot += ps[w * N + l];
-                store_rho(l, tot);
+                for (int w = 0; w < 8; ++w) two_sum(tot, lo, ps[w * N + l]);
+                store_rho(l, tot + lo);
             }
         } else {
             const unsigned tn_log2 = 31 - __clz(F.TN);
@@ -551,10 +554,10 @@ __global__ void __launch_bounds__(kSmallThreads, 1) tail_small_kernel(const __gr
                 const unsigned tile = static_cast<unsigned>(l) >> tn_log2, lane = static_cast<unsigned>(l) & (F.TN - 1);
                 const unsigned b_lo = tabulated ? s_blo[tile] : (tile * F.rpt) / F.rpc;
                 const unsigned b_hi = tabulated ? s_bhi[tile] : ((tile + 1) * F.rpt - 1) / F.rpc;
-                double tot = 0;
+                double tot = 0, lo = 0;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) tot += slot_sum(tile, lane, b_lo, b_hi, w);
-                store_rho(l, tot);
+                for (int w = 0; w < 8; ++w) two_sum(tot, lo, slot_sum(tile, lane, b_lo, b_hi, w));
+                store_rho(l, tot + lo);
             }
         }
     }

@@ -144,7 +144,9 @@ class CudaScheduler:
     def step_host(self, n: int, coeffs: np.ndarray, rho: np.ndarray | None = None, peer: bool = False) -> float:
         """One time step for a history kept on the HOST (the reference GPU drivers' loop body in one call): level n-1 of `coeffs`
         goes to the device, the fused step runs, level n is written into `coeffs`, rho (optional) is filled; returns the energy."""
-        assert coeffs.dtype == np.float64 and coeffs.flags.c_contiguous and coeffs.size >= (n + 1) * self.stride_t
+        assert coeffs.dtype == np.float64 and coeffs.flags.c_contiguous
+        if n > self.conf.Nt or coeffs.size < (n + 1) * self.stride_t:
+            raise RangeError("Time-step out of range.")
         e = C.c_double(0.0)
         self._ck(self._L.nufi_b200_step_host(self._h, n, _ptr(coeffs), _ptr(rho) if rho is not None else None, C.byref(e), 1 if peer else 0))
         return e.value
