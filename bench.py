@@ -46,6 +46,7 @@ SMEM_BYTES_PER_CLK_SM = 128.0  # shared-memory data pipe; tools/microbench.cu me
 RF_CEILING = {(1, False): 0.848, (2, True): 0.809, (2, False): 0.825, (3, True): 0.780, (3, False): 0.793}
 L2_FLUSH_BYTES = 256 << 20
 RHO_TOL = 1e-10
+LEAD_IN = 3  # untimed iterations enqueued directly in front of the timed ones (see timed_region)
 SETTLE_STEPS = 10  # untimed iterations in front of every timed region (at least the W asked for): the first steps after an idle
 # gap run 1-3 % slower (clock / power ramp), config.settle_steps states it
 ALIGN_RANKS = True  # N > 1: a stream-ordered NCCL barrier between the (untimed) L2 flush and every timed step
@@ -344,12 +345,21 @@ def timed_region(runner, n, steps, warmup, flush, torch, dist, sampler=None, ali
     l0 = s.launches
     ctx = sampler if sampler is not None else _Null()
     with ctx:
-        for a, b in ev:
+        # LEAD_IN untimed iterations are enqueued in the same burst in front of the timed ones: the first step after the
+        # synchronisation above starts from an idle GPU and an empty launch queue (no tail to launch behind) and runs 3-8 % slower
+        # than every later one -- a start-up cost of the measurement, not of a run's steps (config.lead_in_steps)
+        for i in range(LEAD_IN + steps):
             with torch.cuda.stream(st):
                 if flush is not None:
                     flush.fill_(1.0)  # L2 flush, untimed
                 if align is not None:  # untimed: the ranks leave the flush together (its duration jitters by microseconds), as
                     dist.all_reduce(align)  # they do in a run without flushes, where every step ends with the exchange
+            if i < LEAD_IN:
+                runner.step(n)
+                if i == LEAD_IN - 1:
+                    l0 = s.launches
+                continue
+            a, b = ev[i - LEAD_IN]
             a.record(st)
             runner.step(n)
             b.record(st)
@@ -728,7 +738,7 @@ def run_gpu_arm(args):
                               "flushed between timed steps (256 MiB fill, untimed; steps timed individually with CUDA events)" +
                               ("; ranks aligned by a stream-ordered NCCL barrier between the flush and each timed step (untimed)"
                                if world > 1 and ALIGN_RANKS else "")),
-                       "settle_steps": max(args.warmup, SETTLE_STEPS),
+                       "settle_steps": max(args.warmup, SETTLE_STEPS), "lead_in_steps": LEAD_IN,
                        "parallelism": (f"quadrature points sharded over {world} GPU(s); rho exchange: " +
                                        ("stores into NVLink peer memory fused into the slot-reduction and tail kernels (no collective call)"
                                         if runner.exchange == "peer-memory" else "NCCL all-reduce")) if world > 1 else "1 GPU",

@@ -182,7 +182,9 @@ int nufi_b200_eval_f(nufi_b200_handle *h, size_t n, size_t npts, const double *p
 int nufi_b200_eval_field(nufi_b200_handle *h, size_t n, int derivative_axis, size_t npts, const double *points_host, double *values_host);
 /* eval_phase_flow (nufi/rho.hpp:98-131, dim1 in the reference; bin/test_nufi_gpu_1d.cpp:155,190,339): the flow map itself --
  * feet[i] = (x.., v..) at t = 0 of the characteristic through points[i] = (x.., v..) at t_n (needs levels 0..n), both
- * [npts][2*dim].  As in the reference nothing is traced for n <= 1, and positions are reduced with L*floor(x/L). */
+ * [npts][2*dim].  As in the reference nothing is traced for n <= 1, and positions are reduced with L*floor(x/L).  The device
+ * traces the periodic image inside [x_min, x_min + L), so the returned position is the reference's whenever x_min is a multiple
+ * of L (every reference configuration has x_min = 0); otherwise it is that position modulo L, shifted into [0, L). */
 int nufi_b200_eval_phase_flow(nufi_b200_handle *h, size_t n, size_t npts, const double *points_host, double *feet_host);
 
 /* ---- device-pointer plumbing for one-process-per-GPU callers (torch.distributed / NCCL host layer) ---- */
