@@ -36,6 +36,10 @@ def read_binary(path):
         magic, version, dim, order, _, nx, ny, nz, n_levels, dt = _HDR.unpack(f.read(64))
         if magic != b"NUFIB200" or version != 1:
             raise ValueError(f"{path}: not a nufi-b200 history")
+        lim = 1 << 20  # do not trust the header: every field bounded before it sizes anything (include/nufi/history_io.hpp)
+        if not (1 <= dim <= 3 and 1 <= order <= 8 and 1 <= nx <= lim and (dim < 2 or 1 <= ny <= lim) and (dim < 3 or 1 <= nz <= lim)
+                and n_levels <= lim):
+            raise ValueError(f"{path}: implausible header")
         coeffs = np.frombuffer(f.read(), dtype=np.float64).copy()
     hdr = dict(dim=dim, order=order, Nx=nx, Ny=ny, Nz=nz, n_levels=n_levels, dt=dt)
     o = order - 1

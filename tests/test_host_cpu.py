@@ -311,6 +311,44 @@ int main(int argc, char** argv){
     assert np.array_equal(history_io.read_text(tmp_path / "h2.txt", 4 * st, header_lines=7), coeffs)
 
 
+def test_history_reader_does_not_trust_the_header(tmp_path):
+    """A corrupt or foreign header (order 0, absurd sizes, a length the file does not have) is refused by both readers before it
+    sizes an allocation; matches() compares a header with the running configuration."""
+    import struct
+
+    from numericalflowiteration_b200 import history_io
+
+    conf = Config3D(Nx=5, Ny=4, Nz=6, Nt=3)
+    st = stride_t(conf)
+    good = tmp_path / "good.bin"
+    history_io.write_binary(good, conf, np.arange(2 * st, dtype=np.float64), 2)
+    raw = open(good, "rb").read()
+    hdr = struct.Struct("<8sIIIIQQQQd")
+    fields = list(hdr.unpack(raw[:64]))
+    cases = {"order0": (3, 0), "dim7": (2, 7), "hugeNx": (5, 1 << 40), "levels": (8, 1 << 19), "truncated": None}
+    src = r'''
+#include <nufi/history_io.hpp>
+int main(int argc, char** argv){
+  std::vector<double> c;
+  try { auto h = nufi::history_io::read_binary(argv[1], c); return nufi::history_io::matches(h, 3, 4, 5, 4, 6) ? 0 : 4; }
+  catch (const std::runtime_error&) { return 7; } }'''
+    open(tmp_path / "r.cpp", "w").write(src)
+    subprocess.run(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-o", str(tmp_path / "r"), str(tmp_path / "r.cpp")], check=True)
+    assert subprocess.run([str(tmp_path / "r"), str(good)]).returncode == 0
+    for name, edit in cases.items():
+        f2 = list(fields)
+        body = raw[64:]
+        if edit is None:
+            body = body[:-8]
+        else:
+            f2[edit[0]] = edit[1]
+        path = tmp_path / f"{name}.bin"
+        open(path, "wb").write(hdr.pack(*f2) + body)
+        with pytest.raises(ValueError):
+            history_io.read_binary(path)
+        assert subprocess.run([str(tmp_path / "r"), str(path)]).returncode == 7, name
+
+
 def test_c_abi_header_is_plain_c(tmp_path):
     """include/nufi_b200.h is the drop-in boundary: plain C (C99, -pedantic clean), no C++ or torch types in any signature."""
     src = tmp_path / "hdr.c"
