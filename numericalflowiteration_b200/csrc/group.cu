@@ -190,7 +190,7 @@ int nufi_b200_group_step(nufi_b200_group *gg, size_t n)
         if (rc) g->err = g->hs[0]->err;
         return rc;
     }
-    if (g->exchange == 0) { // fused: backtrace -> finish+push into every GPU -> tail that waits for the peers' flags
+    if (g->exchange == 0) { // fused: backtrace -> tail that adds this GPU's slots, pushes its sums to every GPU and polls the peers' (peer.cu)
         for (size_t i = 0; i < parts; ++i) {
             int rc = nufi_b200_peer_step(reinterpret_cast<nufi_b200_handle *>(g->hs[i]), n);
             if (rc) { g->err = g->hs[i]->err; return rc; }

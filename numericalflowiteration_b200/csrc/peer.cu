@@ -3,17 +3,19 @@
 // Replaces the reference's fan-in (cuda_kernel::download_rho's blocking copy + host add per device, nufi/cuda_kernel.cu:135-145,
 // nufi/cuda_scheduler.hpp:113-118, and MPI_Allreduce on host buffers, bin/test_nufi_gpu_3d.cpp:158) -- and the NCCL all-reduce
 // this library used first -- by direct stores into peer memory (layout and wire encoding: internal.cuh):
-//   * the backtrace kernel (epilogue mode 3, backtrace_kernel.cuh): the last CTA to finish a tile adds the tile's per-(CTA, tile)
-//     slots in a fixed order and stores the 32 sums into the exchange buffer of EVERY GPU (NVLink stores), every 8-byte word
-//     carrying the step's epoch beside its 32 bits of payload.  Tiles are reduced and pushed in parallel by whichever CTAs finish
-//     them; no system-scope fence, no flag, no serial section: the kernel ends when its CTAs end;
-//   * the field tail (tail_small_kernel / peer_gather_kernel) adds the ranks' sums in rank order, polling every word it loads
-//     until it carries this step's epoch -- it does not even wait for its own GPU's backtrace grid to retire -- so all replicas
-//     compute bit-identical rho, phi and histories with no collective call, no extra launch and no host synchronisation.
+//   * the backtrace kernel is the single-GPU fused step's: it writes its per-(CTA, tile) slots into LOCAL memory as self-validating
+//     words (every 8-byte half carries the step's epoch beside 32 bits of payload) and ends when its CTAs end -- no reduction, no
+//     fence, no flag, no serial section;
+//   * the field tail (tail_small_kernel), resident beside that kernel since its start, adds the local slots in the fixed order as
+//     they land, STORES the per-node sums into the exchange buffer of every other GPU (NVLink stores of the same kind of words),
+//     and adds all ranks' sums in rank order, polling every word it loads until it carries this step's epoch -- so all replicas
+//     compute bit-identical rho, phi and histories with no collective call, no extra launch and no host synchronisation.  Grids too
+//     large for the one-CTA tail: finish_rho_kernel (one block per tile) pushes, peer_gather_kernel polls.
 //     History of this exchange (profiles/r02_peer_exchange.md): r01 = the kernel's LAST CTA reduced all tiles serially and pushed
 //     the result behind a system-scope fence (3.8 us alone) and a flag, ~9 us on a 150 us step; r02 v2/v3 = every CTA pushed its
 //     raw slots and the one-CTA tail added world x (CTAs x tiles) of them -- no sender epilogue, but a tail that grew with the
-//     GPU count (33 us at 8 GPUs).
+//     GPU count (33 us at 8 GPUs); v4 = the last CTA to finish a tile reduced and pushed it (fence + atomic + dependent loads at
+//     the end of every CTA: the kernel 10 us longer).
 // Mapping of the peers' buffers: one process driving all GPUs (nufi_b200_group_*) enables direct peer access; one process per
 // GPU (torchrun) exchanges cudaIpcMemHandle_t through the host layer (nufi_b200_peer_export / _attach).
 #include "internal.cuh"

@@ -844,7 +844,7 @@ int tail_run(Handle *h, size_t n, const double *d_rho_full, bool from_peer)
         return NUFI_B200_OK;
     }
 
-    if (from_peer) { // large grids: gather kernel (waits for the flags, sums in rank order) -> d_rho_full
+    if (from_peer) { // large grids: gather kernel (polls the ranks' self-validating sums, adds in rank order) -> d_rho_full
         int rc = launch_peer_gather(h);
         if (rc) return rc;
         d_rho_full = h->d_rho_full;

@@ -77,7 +77,7 @@ class DistributedStepper:
     def step(self, n: int) -> None:
         """One time step: local backtrace -> exchange of rho -> replicated field tail -> level n."""
         if self.exchange == "peer-memory":
-            self.sched.peer_step(n)  # exchange fused into the kernels (stores into peer memory + flags)
+            self.sched.peer_step(n)  # exchange fused into the kernels (self-validating stores into peer memory)
             return
         self.compute_rho(n)
         self.reduce_rho()
