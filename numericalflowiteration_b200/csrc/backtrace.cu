@@ -10,8 +10,10 @@
 //    hit one rho address with atomics.  A CTA-round is W warp-units of the SAME tile; persistent CTAs (one per
 //    SM) take contiguous runs of CTA-rounds.  Each thread sums f of its node over its velocities in registers;
 //    when the CTA's tile changes the consumer warps combine their sums through shared memory in a fixed order
-//    and write ONE slot per (CTA, tile); a small kernel adds the slots of a tile in a fixed order.  No atomics:
-//    results are run-to-run deterministic.
+//    and write ONE slot per (CTA, tile); the slots of a tile are added in a fixed order by the fused field tail (which
+//    polls them as self-validating words while this grid still runs), by this kernel's last CTA, or by
+//    finish_rho_kernel.  The per-thread and per-CTA sums are compensated (two-sum).  No atomics on data: results
+//    are run-to-run deterministic.
 //  * History access.  Staged variant: a producer warp streams the history newest -> oldest from the HBM/L2-
 //    resident ring into a shared-memory ring of stages with cp.async.bulk (TMA bulk copy, SASS UBLKCP) +
 //    mbarrier full/empty pairs; a stage holds a CHUNK of several consecutive levels so barrier traffic and loop
@@ -20,9 +22,13 @@
 //  * Arithmetic.  Position per dimension = (cell k, centred offset tau in [-1/2,1/2]); floor() and the
 //    float->int conversion (quarter-rate pipes) are replaced by the 1.5*2^52 rounding trick on the FP64 pipe.
 //    The regular full-kick step is the only thing in the inner loop: eval_f's initial half kick and the final
-//    half kick on level 0 are peeled.  1d levels are stored as per-cell quadratics of dt*E (3 doubles per cell,
-//    see tail.cu), so a 1d point-step is 7 FP64 instructions; 2d/3d use the cubic B-spline window (16/64
-//    doubles) with value and derivative bases computed once per dimension and shared by the field components.
+//    half kick on level 0 are peeled.  1d levels are stored as per-cell quadratics of dt*E ([Nx x (p1,p2)] [Nx x p0],
+//    see tail.cu), so a 1d point-step is one 128-bit and one 64-bit load and 7 FP64 instructions; 2d/3d use the
+//    cubic B-spline window (16/64 doubles) with value and derivative bases computed once per dimension and
+//    shared by the field components, or the xpp format (per-row cubics in the x offset: Horner instead of basis).
+//  * Launch.  Programmatic dependent launch in both directions: the field tail becomes resident while this grid
+//    runs; the next step's grid becomes resident while that tail runs and waits (griddepcontrol.wait) before its
+//    first global read.
 #include "backtrace_kernel.cuh"
 
 namespace nufi_b200
