@@ -36,8 +36,8 @@ if ROOT not in sys.path:
 
 FLOP_PER_POINT_STEP = {1: 30.0, 2: 138.0, 3: 431.0}  # SURVEY.md section 8d / App. A.4 (algorithmic, FMA = 2)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE backtrace launch at the default depth, from the committed ncu --set full
-# captures (profiles/r01c_ncu_full_summary.csv, profiles/r02a_ncu_C5-32.csv); the algorithmic figure is n*level_bytes + 16*Nnodes
-NCU_DRAM_TRAFFIC_BYTES = {"C2": 4.98e6, "C3": 3.65e6, "C4": 1.62e6, "C5-16": 1.44e6, "C5-32": 8.73e6}
+# captures of the kernels as shipped (profiles/r02_ncu_full_summary.csv); the algorithmic figure is n*level_bytes + 16*Nnodes
+NCU_DRAM_TRAFFIC_BYTES = {"C1": 4.97e6, "C2": 4.97e6, "C3": 3.65e6, "C4": 1.62e6, "C5-16": 1.45e6, "C5-32": 8.78e6}
 SMEM_BYTES_PER_POINT_STEP = {1: 24.0, 2: 128.0, 3: 512.0}  # coefficients a point gathers per level
 SMEM_BYTES_PER_CLK_SM = 128.0  # shared-memory data pipe; tools/microbench.cu measures 125-127 on this GPU
 # FP64 ceiling of each kernel's hot loop once the register-file operand reads of its DFMAs are counted (a DFMA with 1 / 2 / 3
@@ -704,7 +704,7 @@ def run_gpu_arm(args):
         roofline = {
             "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
             "traffic": NCU_DRAM_TRAFFIC_BYTES.get(args.workload) if (world == 1 and not args.depth) else None,
-            "traffic_source": "profiles/r01c_ncu_full_summary.csv (one ncu --set full capture of this kernel at this depth); bytes per launch",
+            "traffic_source": "profiles/r02_ncu_full_summary.csv (one ncu --set full capture of this kernel at this depth); bytes per launch",
             "kernel": f"backtrace_kernel<{dim}d> [{variant}]", "kernel_ms": m["bt_ms"], "kernel_ms_per_rank": m["bt_ms_per_rank"],
             "kernel_share_of_step": m["bt_ms"] * args.steps / m["t_ms_kernel_timing"],
             "ms_per_step_with_kernel_events": m["t_ms_kernel_timing"] / args.steps,
